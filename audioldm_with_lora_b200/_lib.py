@@ -1,0 +1,94 @@
+"""ctypes binding of libb200ldm.so (the C-ABI declared in include/b200ldm.h).
+
+There is NO fallback: if the shared library is missing or a kernel call fails, this raises.
+PyTorch is only the owner of device memory and streams; every compute call below lands in a
+hand-written sm_100a kernel.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_long, c_void_p
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("B200LDM_LIB", _PKG / "libb200ldm.so"))
+
+_lib: Optional[ctypes.CDLL] = None
+launch_count = 0          # kernels launched through this binding (bench.py's gpu_launches)
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+_PROTOS = {
+    "b200_version": (c_int, []),
+    "b200_last_error": (c_char_p, []),
+    "b200_conv_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                               c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
+                               c_int, c_int, c_int, c_int, c_void_p]),
+    "b200_gn_nslab": (c_int, [c_int]),
+    "b200_groupnorm_silu": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
+                                    c_int, c_void_p, c_void_p, c_void_p]),
+    "b200_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "b200_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "b200_time_class_embed": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200_pack_nchw_to_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_unpack_nhwc_to_nchw": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_upsample_nearest": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_sampler_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int,
+                                  c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_add_noise": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_float,
+                                c_float, c_int, c_float, c_void_p]),
+    "b200_mse_partial": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_void_p]),
+}
+EXPORTS = tuple(_PROTOS)
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise B200Error(f"{LIB_PATH} not found: build it with `python -m audioldm_with_lora_b200.build` "
+                            "(there is no CPU / PyTorch fallback)")
+        lib = ctypes.CDLL(str(LIB_PATH))
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(lib, name)      # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().b200_last_error().decode(errors="replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise B200Error(f"{what} failed (code {rc}): {last_error()}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise B200Error("b200 kernels need CUDA tensors (no CPU fallback)")
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args) -> None:
+    global launch_count
+    rc = getattr(load(), name)(*args)
+    check(rc, name)
+    launch_count += 2 if name == "b200_groupnorm_silu" else 1

@@ -1,0 +1,324 @@
+// Fused multi-head self-attention over the latent sequence for sm_100a (K2).
+//
+//   out[b, s, h*d:(h+1)*d] = softmax(Q_h K_h^T * scale) V_h      (non-causal, no mask, no dropout)
+//
+// One CTA = 128 query rows of one (batch, head).  Per 128-key block:
+//   S = Q K^T     tcgen05.mma 128x128x16 (x d/16), operands in smem, S in TMEM
+//   softmax       4 warps, one query row per thread: tcgen05.ld S, online max / exp2 / sum in fp32,
+//                 P (bf16) written to smem in the UMMA K-major core-matrix layout
+//   O_blk = P V   tcgen05.mma 128 x d x 16 (x 8), V consumed straight from the [Q|K|V] GEMM output
+//                 as an MN-major operand (no transposed copy); O_blk in TMEM
+//   acc = acc * alpha + O_blk   in registers (fp32), folded one block late so the PV MMA overlaps
+//                 the next block's max pass.
+// Q/K/V tiles are fetched by TMA directly from the fused-QKV activation [B, S, 3C] with a 4-D tensor
+// map (8 elems, rows, 16-byte channel chunks, batch): the box lands as 8x16B core matrices, i.e. the
+// no-swizzle UMMA canonical layout, for any head_dim that is a multiple of 16 (32/48/80 for
+// AudioLDM-S, 64/96/160 for -L).  Rows past the end of the sequence are zero-filled by TMA and
+// masked to -inf in the softmax.
+//
+// Replaces F.scaled_dot_product_attention in diffusers AttnProcessor2_0.__call__ (attention-processor
+// API; reached from /root/reference/script/train/train_audioldm_lora.py:539-546, app.py:14).
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+static constexpr int kQ = 128;                 // query rows per CTA
+static constexpr int kKV = 128;                // keys per block
+static constexpr int kAttnThreads = 192;       // warps 0-3 softmax, warp 4 TMA, warp 5 MMA
+static constexpr int kMaxD = 160;
+
+struct AttnParams {
+  int seq, heads, d, batch;
+  int nblk;                 // ceil(seq / 128)
+  int stages;               // K/V ring depth (1 or 2)
+  int tmem_cols;            // 256 (d <= 128) or 512
+  float scale_log2;         // scale * log2(e)
+  __nv_bfloat16* out;
+  int out_ld;               // heads * d
+  int variant;              // bit0: swap LBO/SBO of K-major descs, bit1: swap for the MN-major V desc
+};
+
+template <int D>
+__device__ __forceinline__ void fold_o(uint32_t t_o, float (&acc)[kMaxD], float alpha) {
+#pragma unroll
+  for (int c = 0; c < D / 16; ++c) {
+    uint32_t r[16];
+    tmem_ld_x16(t_o + c * 16, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[c * 16 + j] = acc[c * 16 + j] * alpha + __uint_as_float(r[j]);
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kAttnThreads)
+attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  constexpr int kTileBytes = 128 * D * 2;       // one Q / K / V tile
+  constexpr int kPBytes = kQ * kKV * 2;
+  uint8_t* sQ = smem;
+  uint8_t* sP = sQ + kTileBytes;
+  uint8_t* sKV = sP + kPBytes;                  // stages x {K, V}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + p.stages * 2 * kTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                 // [2]
+  uint64_t* kv_empty = bars + 3;                // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kQ;
+  const int bh = blockIdx.y;
+  const int b = bh / p.heads;
+  const int h = bh % p.heads;
+  const int C8 = p.heads * D / 8;               // 16-byte chunks per Q (or K, or V) section
+  const int chunk_q = h * (D / 8);
+  const int chunk_k = C8 + chunk_q;
+  const int chunk_v = 2 * C8 + chunk_q;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_s = tmem_base;               // S: columns [0, 128)
+  const uint32_t t_o = tmem_base + 128;         // O_blk: columns [128, 128 + D)
+
+  if (warp == 4) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kTileBytes);
+      tma_load_4d(sQ, &tmQKV, q_full, 0, q0, chunk_q, b);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < p.nblk; ++j) {
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        uint8_t* k_dst = sKV + s * 2 * kTileBytes;
+        mbar_expect_tx(&kv_full[s], 2 * kTileBytes);
+        tma_load_4d(k_dst, &tmQKV, &kv_full[s], 0, j * kKV, chunk_k, b);
+        tma_load_4d(k_dst + kTileBytes, &tmQKV, &kv_full[s], 0, j * kKV, chunk_v, b);
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);       // B = V, MN-major
+      // no-swizzle canonical layouts: core matrix = 8 rows x 16 B, contiguous (128 B).
+      //  K-major tile [128 rows][D]: next 8-row group +128 B (SBO), next 8-elem K chunk +2048 B (LBO)
+      //  MN-major V   [128 keys][D]: next 8-key group +128 B (LBO), next 8-elem d chunk +2048 B (SBO)
+      const uint32_t k_lbo = (p.variant & 1) ? 128 : 2048, k_sbo = (p.variant & 1) ? 2048 : 128;
+      const uint32_t v_lbo = (p.variant & 2) ? 2048 : 128, v_sbo = (p.variant & 2) ? 128 : 2048;
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t p_addr = smem_u32(sP);
+      mbar_wait(q_full, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < p.nblk; ++j) {
+        const uint32_t k_addr = smem_u32(sKV + s * 2 * kTileBytes);
+        const uint32_t v_addr = k_addr + kTileBytes;
+        mbar_wait(&kv_full[s], ph);
+        tc_fence_after();
+        // S = Q K^T   (the previous block's softmax finished reading S before it released p_full)
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint64_t a_desc = make_smem_desc(q_addr + k * 4096, k_lbo, k_sbo, SWZ_NONE);
+          const uint64_t b_desc = make_smem_desc(k_addr + k * 4096, k_lbo, k_sbo, SWZ_NONE);
+          umma_bf16_ss(t_s, a_desc, b_desc, idesc_s, k != 0);
+        }
+        umma_commit(s_full);
+        // O_blk = P V
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kKV / 16; ++k) {
+          const uint64_t a_desc = make_smem_desc(p_addr + k * 4096, k_lbo, k_sbo, SWZ_NONE);
+          const uint64_t b_desc = make_smem_desc(v_addr + k * 256, v_lbo, v_sbo, SWZ_NONE);
+          umma_bf16_ss(t_o, a_desc, b_desc, idesc_o, k != 0);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[s]);
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else {
+    // ============================================================ softmax + accumulate (row = thread)
+    const int row = warp * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    float acc[kMaxD];
+#pragma unroll
+    for (int i = 0; i < D; ++i) acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+    for (int j = 0; j < p.nblk; ++j) {
+      const int kvalid = min(kKV, p.seq - j * kKV);
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(t_s + lane_off + c * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float v = (c * 32 + i < kvalid) ? __uint_as_float(r[i]) : -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = exp2f((m_run - m_new) * p.scale_log2);
+      const float neg_m = -m_new * p.scale_log2;
+      // fold the previous block's P V (also guarantees sP is free again)
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+        fold_o<D>(t_o + lane_off, acc, alpha_prev);
+      }
+      // pass 2: p = exp2(s * c - m * c) -> bf16 -> smem (K-major core matrices), row sum
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(t_s + lane_off + c * 32, r);
+        tmem_wait_ld();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, neg_m));
+          pv[i] = (c * 32 + i < kvalid) ? e : 0.f;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          pk.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]);
+          pk.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
+          pk.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]);
+          pk.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
+          // the row sum uses the bf16-rounded probabilities the PV MMA will see
+          sum += bf16_lo(pk.x) + bf16_hi(pk.x) + bf16_lo(pk.y) + bf16_hi(pk.y) + bf16_lo(pk.z) + bf16_hi(pk.z) +
+                 bf16_lo(pk.w) + bf16_hi(pk.w);
+          *reinterpret_cast<uint4*>(sP + (c * 4 + g) * 2048 + row * 16) = pk;
+        }
+      }
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      alpha_prev = alpha;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(o_full, (p.nblk - 1) & 1);
+    tc_fence_after();
+    // last block: its own alpha was already applied to l_run; acc still needs alpha_last
+    fold_o<D>(t_o + lane_off, acc, alpha_prev);
+    const int qrow = q0 + row;
+    if (qrow < p.seq) {
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* o = p.out + (static_cast<size_t>(b) * p.seq + qrow) * p.out_ld + h * D;
+#pragma unroll
+      for (int g = 0; g < D / 8; ++g) {
+        uint4 pk;
+        pk.x = pack_bf16x2(acc[g * 8 + 0] * inv, acc[g * 8 + 1] * inv);
+        pk.y = pack_bf16x2(acc[g * 8 + 2] * inv, acc[g * 8 + 3] * inv);
+        pk.z = pack_bf16x2(acc[g * 8 + 4] * inv, acc[g * 8 + 5] * inv);
+        pk.w = pack_bf16x2(acc[g * 8 + 6] * inv, acc[g * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(o + g * 8) = pk;
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+template <int D>
+static int launch_attention(const CUtensorMap& tm, AttnParams& p, cudaStream_t stream) {
+  constexpr int kTileBytes = 128 * D * 2;
+  const int fixed = kTileBytes + kQ * kKV * 2 + 128 /*barriers*/ + 128 /*align*/;
+  // two resident CTAs per SM when TMEM allows (256 columns each)
+  const int budget = (p.tmem_cols <= 256) ? 110 * 1024 : 220 * 1024;
+  p.stages = (fixed + 2 * 2 * kTileBytes <= budget) ? 2 : 1;
+  const int smem_bytes = fixed + p.stages * 2 * kTileBytes;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail(B200_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 grid((p.seq + kQ - 1) / kQ, p.batch * p.heads);
+  attention_kernel<D><<<grid, kAttnThreads, smem_bytes, stream>>>(tm, p);
+  B200_CHECK_LAUNCH("attention");
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_attention(const void* qkv, void* out, int batch, int seq, int heads, int head_dim, float scale,
+                              int variant, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(qkv && out, "attention: null pointer");
+  B200_CHECK_ARG(batch > 0 && seq > 0 && heads > 0, "attention: empty problem");
+  const int C = heads * head_dim;
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.seq = seq; p.heads = heads; p.d = head_dim; p.batch = batch;
+  p.nblk = (seq + kKV - 1) / kKV;
+  p.tmem_cols = (head_dim <= 128) ? 256 : 512;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.out_ld = C;
+  p.variant = variant;
+
+  CUtensorMap tm;
+  {
+    // dims (innermost first): 8 elems | seq rows | 16-byte chunks across [Q|K|V] | batch
+    uint64_t dims[4] = {8, (uint64_t)seq, (uint64_t)(3 * C / 8), (uint64_t)batch};
+    uint64_t strides[3] = {(uint64_t)3 * C, 8, (uint64_t)seq * 3 * C};
+    uint32_t box[4] = {8, 128, (uint32_t)(head_dim / 8), 1};
+    int rc = make_tmap_bf16(&tm, qkv, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
+  switch (head_dim) {
+    case 32: return launch_attention<32>(tm, p, stream);
+    case 48: return launch_attention<48>(tm, p, stream);
+    case 64: return launch_attention<64>(tm, p, stream);
+    case 80: return launch_attention<80>(tm, p, stream);
+    case 96: return launch_attention<96>(tm, p, stream);
+    case 160: return launch_attention<160>(tm, p, stream);
+    default: return fail(B200_ERR_UNSUPPORTED, "attention: head_dim %d unsupported (32/48/64/80/96/160)", head_dim);
+  }
+}

@@ -1,0 +1,80 @@
+// Host-side helpers: error reporting for the C-ABI and TMA tensor-map encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace b200 {
+
+enum { B200_OK = 0, B200_ERR_ARG = -1, B200_ERR_CUDA = -2, B200_ERR_DRIVER = -3, B200_ERR_UNSUPPORTED = -4 };
+
+inline char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define B200_CHECK_ARG(cond, ...) \
+  do {                            \
+    if (!(cond)) return ::b200::fail(::b200::B200_ERR_ARG, __VA_ARGS__); \
+  } while (0)
+#define B200_CHECK_LAUNCH(name)                                                                   \
+  do {                                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                                         \
+    if (e__ != cudaSuccess)                                                                       \
+      return ::b200::fail(::b200::B200_ERR_CUDA, "%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor, `rank` dims (innermost first), strides in ELEMENTS for dims 1..rank-1.
+inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                          const uint32_t* box, CUtensorMapSwizzle swz) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return fail(B200_ERR_DRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_el[i] * 2;   // bytes, for dims 1..rank-1
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(B200_ERR_ARG, "TMA base not 16B aligned");
+  for (int i = 0; i + 1 < rank; ++i)
+    if (gstr[i] % 16 != 0) return fail(B200_ERR_ARG, "TMA stride %d (%llu B) not multiple of 16", i, (unsigned long long)gstr[i]);
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail(B200_ERR_DRIVER, "cuTensorMapEncodeTiled failed: %d (rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)",
+                (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+                rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+  }
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,346 @@
+// Sampler step, embeddings, layout and fine-tuning elementwise kernels (HBM / latency bound).
+//
+//  * b200_sampler_step: classifier-free-guidance combine + DDIM / PNDM(PLMS) latent update + the
+//    CFG-duplicated bf16 UNet input for the next step, one launch (K13).  Replaces ~12 ATen launches
+//    per step of AudioLDMPipeline.__call__ (/root/reference/app.py:14,
+//    /root/reference/script/inference/generate_audio.py:47-52) and DDIMScheduler.step (scheduler class
+//    pinned at /root/reference/script/train/train_audioldm_lora.py:367).
+//  * b200_time_class_embed: Timesteps -> TimestepEmbedding -> cat with class_embedding(labels) (K12).
+//  * pack / unpack / nearest-upsample layout kernels (K10 and the NCHW<->NHWC boundary).
+//  * b200_add_noise, b200_mse_partial, b200_adamw_flat: fine-tuning step tail (K15),
+//    train_audioldm_lora.py:504,549,563.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------- sampler step
+// table row (8 floats) for step s:
+//   [0] a      [1] b      [2..5] w0..w3 (weights of e_now, hist[h1], hist[h2], hist[h3])
+//   [6] flags  (bit0: x_base = x_saved instead of x ; bit1: save x into x_saved before the update ;
+//               bits 4-6: push slot + 1 (0 = do not store e_now in the history ring))
+//   [7] packed history slots  h1 | h2 << 4 | h3 << 8
+// DDIM (eta = 0): a = sqrt(a_prev / a_t), b = sqrt(1 - a_prev) - sqrt(a_prev (1 - a_t) / a_t), w = (1,0,0,0).
+__global__ void __launch_bounds__(256)
+sampler_step_kernel(const float* __restrict__ eps, float* __restrict__ x, float* __restrict__ x_saved,
+                    float* __restrict__ hist, const float* __restrict__ table, int* __restrict__ step_ptr,
+                    float guidance, int do_cfg, int nb, int hw, int c, int c_pad,
+                    __nv_bfloat16* __restrict__ xin_next, unsigned int* __restrict__ done_ctr) {
+  const int step = *step_ptr;
+  const float* row = table + static_cast<size_t>(step) * 8;
+  const float a = row[0], b = row[1];
+  const float w0 = row[2], w1 = row[3], w2 = row[4], w3 = row[5];
+  const int flags = __float_as_int(row[6]);
+  const int slots = __float_as_int(row[7]);
+  const int push = ((flags >> 4) & 7) - 1;
+  const size_t n = static_cast<size_t>(nb) * hw * c;          // elements of one latent batch
+  const size_t npix = static_cast<size_t>(nb) * hw;
+  // one thread per pixel (c == 8 channels = two float4)
+  for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < npix;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float out8[8];
+    for (int v = 0; v < c; v += 4) {
+      const size_t i = pix * c + v;
+      float4 e;
+      if (do_cfg) {
+        const float4 eu = *reinterpret_cast<const float4*>(eps + i);
+        const float4 et = *reinterpret_cast<const float4*>(eps + n + i);
+        e = make_float4(eu.x + guidance * (et.x - eu.x), eu.y + guidance * (et.y - eu.y),
+                        eu.z + guidance * (et.z - eu.z), eu.w + guidance * (et.w - eu.w));
+      } else {
+        e = *reinterpret_cast<const float4*>(eps + i);
+      }
+      float4 eh = make_float4(w0 * e.x, w0 * e.y, w0 * e.z, w0 * e.w);
+      if (w1 != 0.f) {
+        const float4 hh = *reinterpret_cast<const float4*>(hist + static_cast<size_t>(slots & 15) * n + i);
+        eh.x += w1 * hh.x; eh.y += w1 * hh.y; eh.z += w1 * hh.z; eh.w += w1 * hh.w;
+      }
+      if (w2 != 0.f) {
+        const float4 hh = *reinterpret_cast<const float4*>(hist + static_cast<size_t>((slots >> 4) & 15) * n + i);
+        eh.x += w2 * hh.x; eh.y += w2 * hh.y; eh.z += w2 * hh.z; eh.w += w2 * hh.w;
+      }
+      if (w3 != 0.f) {
+        const float4 hh = *reinterpret_cast<const float4*>(hist + static_cast<size_t>((slots >> 8) & 15) * n + i);
+        eh.x += w3 * hh.x; eh.y += w3 * hh.y; eh.z += w3 * hh.z; eh.w += w3 * hh.w;
+      }
+      if (push >= 0) *reinterpret_cast<float4*>(hist + static_cast<size_t>(push) * n + i) = e;
+      const float4 xc = *reinterpret_cast<const float4*>(x + i);
+      if (flags & 2) *reinterpret_cast<float4*>(x_saved + i) = xc;
+      const float4 xb = (flags & 1) ? *reinterpret_cast<const float4*>(x_saved + i) : xc;
+      const float4 xn = make_float4(a * xb.x + b * eh.x, a * xb.y + b * eh.y, a * xb.z + b * eh.z, a * xb.w + b * eh.w);
+      *reinterpret_cast<float4*>(x + i) = xn;
+      out8[v] = xn.x; out8[v + 1] = xn.y; out8[v + 2] = xn.z; out8[v + 3] = xn.w;
+    }
+    if (xin_next) {
+      for (int v = 0; v < c; v += 8) {
+        uint4 pk;
+        pk.x = pack_bf16x2(out8[v], out8[v + 1]); pk.y = pack_bf16x2(out8[v + 2], out8[v + 3]);
+        pk.z = pack_bf16x2(out8[v + 4], out8[v + 5]); pk.w = pack_bf16x2(out8[v + 6], out8[v + 7]);
+        *reinterpret_cast<uint4*>(xin_next + pix * c_pad + v) = pk;
+        if (do_cfg) *reinterpret_cast<uint4*>(xin_next + (npix + pix) * c_pad + v) = pk;
+      }
+    }
+  }
+  // last block to finish advances the step counter (every block has read it by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(done_ctr, 1u);
+    if (prev == gridDim.x - 1) {
+      *done_ctr = 0;
+      *step_ptr = step + 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- embeddings
+// grid (nchunk, nb); block 256.  Every block recomputes the 1st MLP layer (tproj x ted MACs, tiny).
+__global__ void __launch_bounds__(256)
+time_class_embed_kernel(const float* __restrict__ t_steps, const int* __restrict__ step_ptr, int per_sample,
+                        const float* __restrict__ labels, int tproj, int ted, int class_in,
+                        const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                        const float* __restrict__ b2, const float* __restrict__ wc, const float* __restrict__ bc,
+                        float* __restrict__ emb, __nv_bfloat16* __restrict__ silu_emb) {
+  extern __shared__ float sm[];
+  float* s_sin = sm;                  // [tproj]  ([cos | sin], flip_sin_to_cos=True)
+  float* s_h = sm + tproj;            // [ted]
+  float* s_lab = s_h + ted;           // [class_in]
+  const int bidx = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const float t = per_sample ? t_steps[bidx] : t_steps[step_ptr ? *step_ptr : 0];
+  const int half = tproj / 2;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float freq = expf(-logf(10000.0f) * static_cast<float>(i) / static_cast<float>(half));
+    const float arg = t * freq;
+    s_sin[i] = cosf(arg);
+    s_sin[half + i] = sinf(arg);
+  }
+  for (int i = threadIdx.x; i < class_in; i += blockDim.x) s_lab[i] = labels[static_cast<size_t>(bidx) * class_in + i];
+  __syncthreads();
+  for (int o = warp; o < ted; o += nwarp) {
+    float acc = 0.f;
+    for (int k = lane; k < tproj; k += 32) acc += w1[static_cast<size_t>(o) * tproj + k] * s_sin[k];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) {
+      const float v = acc + b1[o];
+      s_h[o] = v / (1.0f + expf(-v));
+    }
+  }
+  __syncthreads();
+  // this block's slice of the 2*ted outputs
+  const int total = 2 * ted;
+  const int per = (total + gridDim.x - 1) / gridDim.x;
+  const int o_begin = blockIdx.x * per, o_end = min(total, o_begin + per);
+  for (int o = o_begin + warp; o < o_end; o += nwarp) {
+    float acc = 0.f;
+    float bias;
+    if (o < ted) {
+      for (int k = lane; k < ted; k += 32) acc += w2[static_cast<size_t>(o) * ted + k] * s_h[k];
+      bias = b2[o];
+    } else {
+      const int oc = o - ted;
+      for (int k = lane; k < class_in; k += 32) acc += wc[static_cast<size_t>(oc) * class_in + k] * s_lab[k];
+      bias = bc[oc];
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) {
+      const float v = acc + bias;
+      if (emb) emb[static_cast<size_t>(bidx) * total + o] = v;
+      silu_emb[static_cast<size_t>(bidx) * total + o] = __float2bfloat16(v / (1.0f + expf(-v)));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- layout kernels
+__global__ void pack_nchw_to_nhwc_kernel(const float* __restrict__ x, int nb, int c, int hw, int c_pad,
+                                         __nv_bfloat16* __restrict__ y) {
+  const size_t total = static_cast<size_t>(nb) * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t n = i / hw, p = i % hw;
+    for (int ch = 0; ch < c; ++ch) y[i * c_pad + ch] = __float2bfloat16(x[(n * c + ch) * hw + p]);
+  }
+}
+__global__ void unpack_nhwc_to_nchw_kernel(const float* __restrict__ x, int nb, int c, int hw, float* __restrict__ y) {
+  const size_t total = static_cast<size_t>(nb) * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t n = i / hw, p = i % hw;
+    for (int ch = 0; ch < c; ++ch) y[(n * c + ch) * hw + p] = x[i * c + ch];
+  }
+}
+// 16-byte vectors; src index = floor(dst * (in / out)) evaluated in fp32 like ATen's nearest kernel.
+__global__ void upsample_nearest_kernel(const uint4* __restrict__ x, int nb, int h, int w, int cv, int ho, int wo,
+                                        uint4* __restrict__ y) {
+  const float sh = static_cast<float>(h) / static_cast<float>(ho);
+  const float sw = static_cast<float>(w) / static_cast<float>(wo);
+  const size_t total = static_cast<size_t>(nb) * ho * wo * cv;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % cv);
+    size_t r = i / cv;
+    const int xo = static_cast<int>(r % wo);
+    r /= wo;
+    const int yo = static_cast<int>(r % ho);
+    const int n = static_cast<int>(r / ho);
+    const int ys = min(static_cast<int>(floorf(yo * sh)), h - 1);
+    const int xs = min(static_cast<int>(floorf(xo * sw)), w - 1);
+    y[i] = x[((static_cast<size_t>(n) * h + ys) * w + xs) * cv + v];
+  }
+}
+
+// ---------------------------------------------------------------------------------- fine-tuning tail
+__global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                 const float* __restrict__ sa, const float* __restrict__ sb, int nb, size_t per,
+                                 float* __restrict__ out) {
+  const size_t total = static_cast<size_t>(nb) * per;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / per;
+    out[i] = sa[b] * x0[i] + sb[b] * noise[i];
+  }
+}
+__global__ void __launch_bounds__(256)
+mse_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, float* __restrict__ out) {
+  float s = 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float d = a[i] - b[i];
+    s += d * d;
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    s = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+  }
+}
+// torch.optim.AdamW semantics (decoupled weight decay, bias correction), grad pre-scaled by grad_scale
+// (1/world after the NCCL sum all-reduce).
+__global__ void adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                  float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
+                                  float bc1, float bc2, float gs) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float gr = g[i] * gs;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = b1 * m[i] + (1.0f - b1) * gr;
+    const float vi = b2 * v[i] + (1.0f - b2) * gr * gr;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi;
+  }
+}
+
+static inline int grid_for(size_t n, int block) {
+  size_t g = (n + block - 1) / block;
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+__device__ unsigned int g_sampler_done_ctr = 0;
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_version(void) { return 100; }
+extern "C" const char* b200_last_error(void) { return last_error_buf(); }
+
+extern "C" int b200_sampler_step(const float* eps, float* x, float* x_saved, float* hist, const float* table,
+                                 int* step_ptr, float guidance, int do_cfg, int nb, int hw, int c, int c_pad,
+                                 void* xin_next, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(eps && x && table && step_ptr, "sampler_step: null pointer");
+  B200_CHECK_ARG(c == 8 && c_pad % 8 == 0 && c_pad >= c, "sampler_step: c=%d c_pad=%d unsupported", c, c_pad);
+  B200_CHECK_ARG(nb > 0 && hw > 0, "sampler_step: empty latents");
+  unsigned int* ctr = nullptr;
+  cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), g_sampler_done_ctr);
+  const size_t npix = static_cast<size_t>(nb) * hw;
+  sampler_step_kernel<<<grid_for(npix, 256), 256, 0, stream>>>(eps, x, x_saved, hist, table, step_ptr, guidance, do_cfg,
+                                                              nb, hw, c, c_pad,
+                                                              reinterpret_cast<__nv_bfloat16*>(xin_next), ctr);
+  B200_CHECK_LAUNCH("sampler_step");
+  return B200_OK;
+}
+
+extern "C" int b200_time_class_embed(const float* t_steps, const int* step_ptr, int per_sample, const float* labels,
+                                     int nb, int tproj, int ted, int class_in, const float* w1, const float* b1,
+                                     const float* w2, const float* b2, const float* wc, const float* bc, float* emb,
+                                     void* silu_emb, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(t_steps && labels && w1 && b1 && w2 && b2 && wc && bc && silu_emb, "time_class_embed: null pointer");
+  B200_CHECK_ARG(nb > 0 && tproj % 2 == 0 && ted > 0 && class_in > 0, "time_class_embed: bad dims");
+  const size_t smem = sizeof(float) * (tproj + ted + class_in);
+  time_class_embed_kernel<<<dim3(16, nb), 256, smem, stream>>>(t_steps, step_ptr, per_sample, labels, tproj, ted,
+                                                               class_in, w1, b1, w2, b2, wc, bc, emb,
+                                                               reinterpret_cast<__nv_bfloat16*>(silu_emb));
+  B200_CHECK_LAUNCH("time_class_embed");
+  return B200_OK;
+}
+
+extern "C" int b200_pack_nchw_to_nhwc(const float* x, int nb, int c, int hw, int c_pad, void* y, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x && y && nb > 0 && c > 0 && hw > 0 && c_pad >= c, "pack_nchw_to_nhwc: bad args");
+  pack_nchw_to_nhwc_kernel<<<grid_for(static_cast<size_t>(nb) * hw, 256), 256, 0, stream>>>(
+      x, nb, c, hw, c_pad, reinterpret_cast<__nv_bfloat16*>(y));
+  B200_CHECK_LAUNCH("pack_nchw_to_nhwc");
+  return B200_OK;
+}
+extern "C" int b200_unpack_nhwc_to_nchw(const float* x, int nb, int c, int hw, float* y, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x && y && nb > 0 && c > 0 && hw > 0, "unpack_nhwc_to_nchw: bad args");
+  unpack_nhwc_to_nchw_kernel<<<grid_for(static_cast<size_t>(nb) * hw, 256), 256, 0, stream>>>(x, nb, c, hw, y);
+  B200_CHECK_LAUNCH("unpack_nhwc_to_nchw");
+  return B200_OK;
+}
+extern "C" int b200_upsample_nearest(const void* x, int nb, int h, int w, int c, int ho, int wo, void* y,
+                                     void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x && y && nb > 0 && h > 0 && w > 0 && ho > 0 && wo > 0 && c % 8 == 0, "upsample_nearest: bad args");
+  const size_t total = static_cast<size_t>(nb) * ho * wo * (c / 8);
+  upsample_nearest_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), nb, h, w, c / 8,
+                                                                   ho, wo, reinterpret_cast<uint4*>(y));
+  B200_CHECK_LAUNCH("upsample_nearest");
+  return B200_OK;
+}
+
+extern "C" int b200_add_noise(const float* x0, const float* noise, const float* sqrt_ac, const float* sqrt_1mac, int nb,
+                              int c, int hw, float* out_nchw, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x0 && noise && sqrt_ac && sqrt_1mac && out_nchw && nb > 0, "add_noise: bad args");
+  const size_t per = static_cast<size_t>(c) * hw;
+  add_noise_kernel<<<grid_for(per * nb, 256), 256, 0, stream>>>(x0, noise, sqrt_ac, sqrt_1mac, nb, per, out_nchw);
+  B200_CHECK_LAUNCH("add_noise");
+  return B200_OK;
+}
+extern "C" int b200_mse_partial(const float* pred, const float* target, long n, float* out_sum, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(pred && target && out_sum && n > 0, "mse_partial: bad args");
+  mse_partial_kernel<<<grid_for(static_cast<size_t>(n), 256), 256, 0, stream>>>(pred, target, static_cast<size_t>(n),
+                                                                               out_sum);
+  B200_CHECK_LAUNCH("mse_partial");
+  return B200_OK;
+}
+extern "C" int b200_adamw_flat(float* param, const float* grad, float* m, float* v, long n, float lr, float beta1,
+                               float beta2, float eps, float weight_decay, int step, float grad_scale,
+                               void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(param && grad && m && v && n > 0 && step >= 1, "adamw_flat: bad args");
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  adamw_flat_kernel<<<grid_for(static_cast<size_t>(n), 256), 256, 0, stream>>>(
+      param, grad, m, v, static_cast<size_t>(n), lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
+  B200_CHECK_LAUNCH("adamw_flat");
+  return B200_OK;
+}

@@ -1,0 +1,179 @@
+"""Typed Python wrappers over the C-ABI kernels (shape checks + pointer marshalling only).
+
+Every function launches hand-written sm_100a kernels from libb200ldm.so on torch's current CUDA
+stream; tensors are borrowed, outputs are caller-allocated.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream
+
+Tensor = torch.Tensor
+NUM_SMS = 148
+
+
+@dataclass
+class PackedWeight:
+    """bf16 [n_pad, K] K-major weight for b200_conv_gemm plus its epilogue vectors."""
+    w: Tensor
+    bias: Optional[Tensor]        # fp32 [n_pad] (tile-interleaved like w when geglu)
+    n_valid: int                  # output columns actually stored
+    block_n: int
+    ntaps: int
+    c0: int
+    c1: int = 0
+    c2: int = 0
+    geglu: bool = False
+
+    @property
+    def n_pad(self) -> int:
+        return self.w.shape[0]
+
+    @property
+    def k(self) -> int:
+        return self.w.shape[1]
+
+
+def box_rows(h: int, w: int, nb: int) -> Tuple[int, int]:
+    """Mirror of pick_box() in conv_gemm.cu: (rows of H, images) covered by one 128-pixel tile."""
+    best, out = None, (1, 1)
+    bh = 1
+    while bh * w <= 128:
+        bni = 128 // (w * bh)
+        if bni <= 256:
+            tiles = math.ceil(h / bh) * math.ceil(nb / bni)
+            if best is None or tiles < best or (tiles == best and bni == 1):
+                best, out = tiles, (bh, bni)
+        bh *= 2
+    return out
+
+
+def num_m_tiles(nb: int, h: int, w: int) -> int:
+    bh, bni = box_rows(h, w, nb)
+    return math.ceil(h / bh) * math.ceil(nb / bni)
+
+
+def choose_block_n(n: int, m_tiles: int, geglu: bool = False) -> int:
+    """Tile width minimising (waves x per-tile cost) on 148 SMs; n is padded up to a multiple of it."""
+    best, best_cost = 32, None
+    step = 64 if geglu else 32
+    for bn in range(step, 257, step):
+        n_tiles = math.ceil(n / bn)
+        waves = math.ceil(m_tiles * n_tiles / NUM_SMS)
+        # per-tile time ~ MMA time (prop. to bn, floor at 64 columns: smem-read bound) + fixed overhead
+        cost = waves * (max(bn, 64) + 24) * (1.0 + 0.02 * (n_tiles * bn - n) / max(n, 1))
+        if best_cost is None or cost < best_cost - 1e-9 or (abs(cost - best_cost) < 1e-9 and bn > best):
+            best, best_cost = bn, cost
+    return best
+
+
+def conv_gemm(pw: PackedWeight, a0: Tensor, nb: int, h: int, w: int, out: Tensor, *, a1: Optional[Tensor] = None,
+              a2: Optional[Tensor] = None, stride: int = 1, rowvec: Optional[Tensor] = None, rowvec_ld: int = 0,
+              residual: Optional[Tensor] = None, out_ld: Optional[int] = None, max_ctas: int = 0) -> Tensor:
+    """out[pix, :n_valid] = epilogue(implicit GEMM); see include/b200ldm.h::b200_conv_gemm."""
+    assert a0.dtype == torch.bfloat16 and a0.is_contiguous()
+    assert a0.numel() == nb * h * w * pw.c0, (a0.shape, nb, h, w, pw.c0)
+    if pw.c1:
+        assert a1 is not None and a1.numel() == nb * h * w * pw.c1 and a1.dtype == torch.bfloat16
+    if pw.c2:
+        assert a2 is not None and a2.numel() == nb * h * w * pw.c2 and a2.dtype == torch.bfloat16
+    out_fp32 = out.dtype == torch.float32
+    assert out_fp32 or out.dtype == torch.bfloat16
+    ld = out_ld if out_ld is not None else pw.n_valid
+    res_ld = 0
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16
+        res_ld = pw.n_valid
+    call("b200_conv_gemm", ptr(a0), pw.c0, ptr(a1) if pw.c1 else None, pw.c1, ptr(a2) if pw.c2 else None, pw.c2,
+         nb, h, w, pw.ntaps, stride, ptr(pw.w), pw.n_pad, pw.n_valid, ptr(pw.bias), ptr(rowvec), rowvec_ld,
+         ptr(residual), res_ld, ptr(out), ld, int(out_fp32), int(pw.geglu), pw.block_n, max_ctas, stream())
+    return out
+
+
+def gn_partial_floats(nb: int, hw: int, groups: int = 32) -> int:
+    return nb * _lib.load().b200_gn_nslab(hw) * groups * 2
+
+
+def groupnorm_silu(x0: Tensor, c0: int, x1: Optional[Tensor], c1: int, nb: int, hw: int, gamma: Tensor, beta: Tensor,
+                   eps: float, silu: bool, partial: Tensor, y: Tensor, groups: int = 32) -> Tensor:
+    assert x0.dtype == torch.bfloat16 and y.dtype == torch.bfloat16 and partial.dtype == torch.float32
+    assert partial.numel() >= gn_partial_floats(nb, hw, groups)
+    assert gamma.numel() == c0 + c1 and gamma.dtype == torch.float32
+    call("b200_groupnorm_silu", ptr(x0), c0, ptr(x1) if c1 else None, c1, nb, hw, groups, ptr(gamma), ptr(beta),
+         float(eps), int(silu), ptr(partial), ptr(y), stream())
+    return y
+
+
+def layernorm(x: Tensor, m: int, c: int, gamma: Tensor, beta: Tensor, eps: float, y: Tensor) -> Tensor:
+    assert x.dtype == torch.bfloat16 and y.dtype == torch.bfloat16
+    call("b200_layernorm", ptr(x), m, c, ptr(gamma), ptr(beta), float(eps), ptr(y), stream())
+    return y
+
+
+def attention(qkv: Tensor, out: Tensor, batch: int, seq: int, heads: int, head_dim: int,
+              scale: Optional[float] = None, variant: int = 0) -> Tensor:
+    assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+    assert qkv.numel() == batch * seq * 3 * heads * head_dim
+    if scale is None:
+        scale = head_dim ** -0.5
+    call("b200_attention", ptr(qkv), ptr(out), batch, seq, heads, head_dim, float(scale), variant, stream())
+    return out
+
+
+def time_class_embed(t_steps: Tensor, step_ptr: Optional[Tensor], per_sample: bool, labels: Tensor, nb: int,
+                     tproj: int, ted: int, class_in: int, w1, b1, w2, b2, wc, bc, emb: Optional[Tensor],
+                     silu_emb: Tensor) -> None:
+    assert t_steps.dtype == torch.float32 and labels.dtype == torch.float32 and silu_emb.dtype == torch.bfloat16
+    call("b200_time_class_embed", ptr(t_steps), ptr(step_ptr), int(per_sample), ptr(labels), nb, tproj, ted, class_in,
+         ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(wc), ptr(bc), ptr(emb), ptr(silu_emb), stream())
+
+
+def pack_nchw_to_nhwc(x: Tensor, nb: int, c: int, hw: int, c_pad: int, y: Tensor) -> Tensor:
+    assert x.dtype == torch.float32 and y.dtype == torch.bfloat16 and x.is_contiguous()
+    call("b200_pack_nchw_to_nhwc", ptr(x), nb, c, hw, c_pad, ptr(y), stream())
+    return y
+
+
+def unpack_nhwc_to_nchw(x: Tensor, nb: int, c: int, hw: int, y: Tensor) -> Tensor:
+    assert x.dtype == torch.float32 and y.dtype == torch.float32
+    call("b200_unpack_nhwc_to_nchw", ptr(x), nb, c, hw, ptr(y), stream())
+    return y
+
+
+def upsample_nearest(x: Tensor, nb: int, h: int, w: int, c: int, ho: int, wo: int, y: Tensor) -> Tensor:
+    assert x.dtype == torch.bfloat16 and y.dtype == torch.bfloat16
+    call("b200_upsample_nearest", ptr(x), nb, h, w, c, ho, wo, ptr(y), stream())
+    return y
+
+
+def sampler_step(eps: Tensor, x: Tensor, x_saved: Optional[Tensor], hist: Optional[Tensor], table: Tensor,
+                 step_ptr: Tensor, guidance: float, do_cfg: bool, nb: int, hw: int, c: int, c_pad: int,
+                 xin_next: Optional[Tensor]) -> None:
+    assert eps.dtype == torch.float32 and x.dtype == torch.float32 and table.dtype == torch.float32
+    assert step_ptr.dtype == torch.int32
+    call("b200_sampler_step", ptr(eps), ptr(x), ptr(x_saved), ptr(hist), ptr(table), ptr(step_ptr), float(guidance),
+         int(do_cfg), nb, hw, c, c_pad, ptr(xin_next), stream())
+
+
+def add_noise(x0: Tensor, noise: Tensor, sqrt_ac: Tensor, sqrt_1mac: Tensor, out: Tensor) -> Tensor:
+    nb, c = x0.shape[0], x0.shape[1]
+    hw = x0[0, 0].numel()
+    call("b200_add_noise", ptr(x0), ptr(noise), ptr(sqrt_ac), ptr(sqrt_1mac), nb, c, hw, ptr(out), stream())
+    return out
+
+
+def adamw_flat(param: Tensor, grad: Tensor, m: Tensor, v: Tensor, lr: float, beta1: float, beta2: float, eps: float,
+               weight_decay: float, step: int, grad_scale: float = 1.0) -> None:
+    assert all(t.dtype == torch.float32 and t.is_contiguous() for t in (param, grad, m, v))
+    call("b200_adamw_flat", ptr(param), ptr(grad), ptr(m), ptr(v), param.numel(), lr, beta1, beta2, eps, weight_decay,
+         step, grad_scale, stream())
+
+
+def mse_partial(pred: Tensor, target: Tensor, out_sum: Tensor) -> None:
+    call("b200_mse_partial", ptr(pred), ptr(target), pred.numel(), ptr(out_sum), stream())

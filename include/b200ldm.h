@@ -1,0 +1,112 @@
+/* b200ldm.h -- C-ABI of libb200ldm.so: hand-written sm_100a kernels for the LoRA-adapted AudioLDM
+ * UNet denoising loop.
+ *
+ * The reference (2025-comprehensive-design/AudioLDM-with-LoRA) is pure Python and owns no FFI; every
+ * FLOP of this path runs inside diffusers / peft / torch ATen.  Each entry point below therefore
+ * cites the reference CALL SITE that reaches the replaced ATen op(s) and the third-party routine
+ * that issues them (diffusers 0.32.2 / peft 0.13.2, pinned at /root/reference/requirements.txt:24,90).
+ *
+ * Conventions: plain pointers + sizes, no torch types.  All pointers are DEVICE pointers unless
+ * stated otherwise; the caller owns every buffer; nothing allocates, nothing synchronises; launches
+ * go to `stream` (a cudaStream_t passed as void*).  Activations are NHWC bf16 ([N, H, W, C], C
+ * innermost) -- a [B, S, C] token matrix is the same memory.  Return 0 on success, a negative
+ * B200_ERR_* code otherwise; b200_last_error() gives the message of the calling thread's last
+ * failure.
+ */
+#ifndef B200LDM_H
+#define B200LDM_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_ARG (-1)
+#define B200_ERR_CUDA (-2)
+#define B200_ERR_DRIVER (-3)
+#define B200_ERR_UNSUPPORTED (-4)
+
+int b200_version(void);
+const char* b200_last_error(void);
+
+/* Implicit-GEMM convolution / linear layer on tcgen05 tensor cores (TMA-fed, TMEM accumulator).
+ *   out[pix, n] = epi( sum_seg sum_tap sum_c A_seg[pix @ tap, c] * wpacked[n, k(seg,tap,c)] )
+ * a0 [nb,h,w,c0] carries ntaps (1 or 9: 3x3, pad 1) taps; a1/a2 (nullable, c1/c2 channels) are extra
+ * 1-tap K segments: the ResNet 1x1 conv_shortcut over cat([h, skip]) and the rank-r LoRA branch
+ * [x | x.A^T] . [W | s.B]^T ride in the same accumulator.  wpacked is bf16 [n_pad, K] (K-major,
+ * K = ntaps*c0 + c1 + c2).  Epilogue: + bias[n] + rowvec[image, n] (timestep/class embedding
+ * projection) + residual[pix, n]; geglu: tile columns are [values | gates] and out = v * gelu(g).
+ * stride == 2 keeps only even (h, w) pixels (Downsample2D).  out is bf16 or fp32, leading dim out_ld.
+ * Replaces F.conv2d / F.linear (+ peft lora.Linear.forward, + GEGLU, + residual adds) under
+ * UNet2DConditionModel.forward: /root/reference/script/train/train_audioldm_lora.py:539-546,
+ * /root/reference/script/inference/generate_audio.py:47-52 (LoRA config :21-29), /root/reference/app.py:14. */
+int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, const void* a2, int c2, int nb, int h, int w,
+                   int ntaps, int stride, const void* wpacked, int n_pad, int n_valid, const float* bias,
+                   const float* rowvec, int rowvec_ld, const void* residual, int res_ld, void* out, int out_ld,
+                   int out_fp32, int geglu, int block_n, int max_ctas, void* stream);
+
+/* GroupNorm (+ optional SiLU) over one or two NHWC sources (cat along C is never materialised).
+ * partial: scratch of nb * b200_gn_nslab(hw) * groups * 2 floats.
+ * Replaces F.group_norm + F.silu in ResnetBlock2D / Transformer2DModel.norm / conv_norm_out
+ * (diffusers, via train_audioldm_lora.py:539-546). */
+int b200_gn_nslab(int hw);
+int b200_groupnorm_silu(const void* x0, int c0, const void* x1, int c1, int nb, int hw, int groups,
+                        const float* gamma, const float* beta, float eps, int silu, float* partial, void* y,
+                        void* stream);
+
+/* LayerNorm over the last dim of a [m, c] bf16 matrix.  Replaces F.layer_norm in
+ * BasicTransformerBlock.norm1/2/3 (diffusers, via train_audioldm_lora.py:539-546). */
+int b200_layernorm(const void* x, int m, int c, const float* gamma, const float* beta, float eps, void* y,
+                   void* stream);
+
+/* Fused multi-head self-attention softmax(Q K^T * scale) V over the latent sequence.
+ * qkv: bf16 [batch, seq, 3*heads*head_dim] = [Q | K | V] columns, head-major inside each;
+ * out: bf16 [batch, seq, heads*head_dim].  variant: 0 (debug knob for descriptor conventions).
+ * Replaces F.scaled_dot_product_attention inside AttnProcessor2_0.__call__ (diffusers attention
+ * processor API; LoRA targets at train_audioldm_lora.py:378-385, generate_audio.py:21-29). */
+int b200_attention(const void* qkv, void* out, int batch, int seq, int heads, int head_dim, float scale,
+                   int variant, void* stream);
+
+/* Timestep / class embedding (K12): emb = cat([time_embedding(sinusoid(t)), class_embedding(labels)]).
+ * t_steps: device float table; step_ptr: device int (nullable => index 0); t index = *step_ptr when
+ * per_sample == 0, else t_steps[b].  Writes emb fp32 [nb, 2*ted] (nullable) and silu(emb) bf16
+ * [nb, 2*ted].  Weights fp32 row-major [out, in].
+ * Replaces Timesteps + TimestepEmbedding + class_embedding in UNet2DConditionModel.forward
+ * (class_labels=prompt_embeds: train_audioldm_lora.py:543). */
+int b200_time_class_embed(const float* t_steps, const int* step_ptr, int per_sample, const float* labels, int nb,
+                          int tproj, int ted, int class_in, const float* w1, const float* b1, const float* w2,
+                          const float* b2, const float* wc, const float* bc, float* emb, void* silu_emb,
+                          void* stream);
+
+/* Layout helpers.  nchw fp32 [nb, c, hw] -> nhwc bf16 [nb, hw, c_pad] (only the first c channels are
+ * written); nhwc fp32 [nb, hw, c] -> nchw fp32; nearest-neighbour resize of NHWC bf16
+ * (src index = floor(dst * in / out), F.interpolate(mode="nearest") in Upsample2D). */
+int b200_pack_nchw_to_nhwc(const float* x, int nb, int c, int hw, int c_pad, void* y, void* stream);
+int b200_unpack_nhwc_to_nchw(const float* x, int nb, int c, int hw, float* y, void* stream);
+int b200_upsample_nearest(const void* x, int nb, int h, int w, int c, int ho, int wo, void* y, void* stream);
+
+/* Sampler step (K13): classifier-free-guidance combine + DDIM / PNDM(PLMS) latent update, fused.
+ *   e = e_u + g (e_t - e_u)            (eps fp32 NHWC [2*nb, hw, c]: first half uncond; g <= 1: [nb,...] only cond)
+ *   ehat = sum_i w[i] * {e, hist[h1], hist[h2], hist[h3]}      x' = a * x_base + b * ehat
+ * with per-step rows of `table` (8 floats: a, b, w0..w3, flags, hist slots; see sampler.cu) indexed by
+ * *step_ptr, which the kernel increments.  x (fp32 NHWC state) is updated in place and the next
+ * CFG-duplicated UNet input is written as bf16 NHWC with c_pad channels.
+ * Replaces noise_pred chunk/guidance + DDIMScheduler.step inside AudioLDMPipeline.__call__
+ * (/root/reference/app.py:14, generate_audio.py:47-52; scheduler class pinned train_audioldm_lora.py:367). */
+int b200_sampler_step(const float* eps, float* x, float* x_saved, float* hist, const float* table, int* step_ptr,
+                      float guidance, int do_cfg, int nb, int hw, int c, int c_pad, void* xin_next, void* stream);
+
+/* DDIMScheduler.add_noise (train_audioldm_lora.py:504): out = sa[b]*x0 + sb[b]*noise, fp32 NCHW in,
+ * also writes the bf16 NHWC c_pad-channel UNet input. */
+int b200_add_noise(const float* x0, const float* noise, const float* sqrt_ac, const float* sqrt_1mac, int nb, int c,
+                   int hw, float* out_nchw, void* stream);
+
+/* LoRA fine-tuning tail (train_audioldm_lora.py:549-565): fused multi-tensor AdamW over a flat fp32
+ * arena; and sum((pred-target)^2) partial reduction for F.mse_loss. */
+int b200_adamw_flat(float* param, const float* grad, float* m, float* v, long n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, float grad_scale, void* stream);
+int b200_mse_partial(const float* pred, const float* target, long n, float* out_sum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
