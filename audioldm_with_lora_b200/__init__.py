@@ -1,0 +1,19 @@
+"""B200-native hot path of AudioLDM-with-LoRA: the LoRA-adapted UNet denoising loop behind the
+diffusers attention-processor / LoRA-loader API and the AudioLDMPipeline call signature.
+
+Compute runs in hand-written sm_100a kernels (csrc/, C-ABI in include/b200ldm.h); PyTorch owns
+device memory and streams only.  There is no CPU or PyTorch fallback for the hot path.
+"""
+from .arch import AUDIOLDM_L, AUDIOLDM_S, CONFIGS, UNetConfig
+from .lora import (LoraConfig, convert_state_dict_to_diffusers, parse_lora_state_dict, to_peft_state_dict)
+from .model import (Attention, B200AttnProcessor, LoraLinear, UNet2DConditionModel, UNet2DConditionOutput,
+                    get_peft_model, get_peft_model_state_dict)
+from .pipeline import AudioLDMPipeline, AudioPipelineOutput
+from .scheduler import DDIMScheduler, PNDMScheduler
+
+__all__ = [
+    "AUDIOLDM_L", "AUDIOLDM_S", "CONFIGS", "UNetConfig", "LoraConfig", "convert_state_dict_to_diffusers",
+    "parse_lora_state_dict", "to_peft_state_dict", "Attention", "B200AttnProcessor", "LoraLinear",
+    "UNet2DConditionModel", "UNet2DConditionOutput", "get_peft_model", "get_peft_model_state_dict",
+    "AudioLDMPipeline", "AudioPipelineOutput", "DDIMScheduler", "PNDMScheduler",
+]

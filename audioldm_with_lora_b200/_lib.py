@@ -87,8 +87,17 @@ def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name: str, *args) -> None:
+PROFILE = None            # set to a list to record (name, start_event, end_event, info) per call
+
+
+def call(name: str, *args, info=None) -> None:
     global launch_count
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(load(), name)(*args)
     check(rc, name)
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append((name, e0, e1, info))
     launch_count += 2 if name == "b200_groupnorm_silu" else 1

@@ -95,6 +95,7 @@ class UNetEngine:
         self._plans: Dict[Tuple[int, int, int], dict] = {}
         self._small: Dict[str, Tensor] = {}
         self.attn_variant = 0
+        self.weights_version = 0      # bumped whenever packed device weights are (re)built
         self.arena: Optional[Arena] = None
         self._init_small()
 
@@ -130,7 +131,7 @@ class UNetEngine:
 
     def _pw(self, segs, bias, m_tiles, ntaps, c0, c1=0, c2=0, geglu=False, block_n=None) -> PackedWeight:
         n = segs[0].shape[0]
-        bn = block_n or ops.choose_block_n(n // 2 if False else n, m_tiles, geglu)
+        bn = block_n or ops.choose_block_n(n, m_tiles, geglu)
         return packing.pack(segs, bias, bn, ntaps, c0, c1, c2, geglu, device=self.device)
 
     def _build_plan(self, nb: int, h: int, w: int) -> dict:
@@ -172,8 +173,8 @@ class UNetEngine:
             W[b + ".ff.net.2"] = self._pw([sd[b + ".ff.net.2.weight"]], sd[b + ".ff.net.2.bias"], mt, 1, 4 * c)
 
         lvl_of: Dict[str, int] = {}
-        W["conv_in"] = None
         conv3("conv_in", 0, LATENT_C_PAD)
+        W["conv_in"].alg_macs_per_row = float(cfg.block_out_channels[0] * 9 * cfg.in_channels)
         for i, stages in enumerate(g.down):
             for s in stages:
                 resnet(s.resnet, i); lvl_of[s.resnet.name] = i
@@ -208,6 +209,7 @@ class UNetEngine:
         return plan
 
     def _pack_attention(self, plan: dict) -> None:
+        self.weights_version += 1
         sd, W, sizes, nb = self.sd, plan["W"], plan["sizes"], plan["nb"]
         for t in self.graph.transformers():
             lvl = plan["lvl_of"][t.name]
@@ -222,8 +224,11 @@ class UNetEngine:
                     kp = packing.lora_pad(sum(x.shape[0] for x in a_list if x is not None))
                     seg = packing.lora_up_segment([e.B if e else None for e in ents], a_list,
                                                   [e.scaling * self.lora_scale if e else 0.0 for e in ents], c)
+                    r_tot = sum(x.shape[0] for x in a_list if x is not None)
                     W[p + ".lora_down_qkv"] = packing.pack_lora_down(a_list, c, device=self.device)
+                    W[p + ".lora_down_qkv"].alg_macs_per_row = float(r_tot * c)
                     W[p + ".qkv"] = self._pw([wqkv, seg], None, mt, 1, c, kp)
+                    W[p + ".qkv"].alg_macs_per_row = float(3 * c * c + r_tot * c)
                 else:
                     W.pop(p + ".lora_down_qkv", None)
                     W[p + ".qkv"] = self._pw([wqkv], None, mt, 1, c)
@@ -233,7 +238,9 @@ class UNetEngine:
                     kp = packing.lora_pad(eo.A.shape[0])
                     seg = packing.lora_up_segment([eo.B], [eo.A], [eo.scaling * self.lora_scale], c)
                     W[p + ".lora_down_o"] = packing.pack_lora_down([eo.A], c, device=self.device)
+                    W[p + ".lora_down_o"].alg_macs_per_row = float(eo.A.shape[0] * c)
                     W[p + ".to_out"] = self._pw([wo, seg], bo, mt, 1, c, kp)
+                    W[p + ".to_out"].alg_macs_per_row = float(c * c + eo.A.shape[0] * c)
                 else:
                     W.pop(p + ".lora_down_o", None)
                     W[p + ".to_out"] = self._pw([wo], bo, mt, 1, c)

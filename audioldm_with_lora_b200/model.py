@@ -305,6 +305,11 @@ class UNet2DConditionModel(nn.Module):
     def lora_state_dict(self, adapter_name: Optional[str] = None) -> Dict[str, Tensor]:
         return to_peft_state_dict(self._adapters, adapter_name)
 
+    def custom_attn_processors(self) -> Optional[dict]:
+        """{attention path: module} for modules whose processor is not the native one."""
+        custom = {p: a for p, a in self._attn.items() if not isinstance(a.processor, B200AttnProcessor)}
+        return custom or None
+
     # ------------------------------------------------------------------ forward
     def _sync_engine_lora(self, scale: float) -> None:
         self.engine.set_lora_scale(scale)
@@ -321,8 +326,8 @@ class UNet2DConditionModel(nn.Module):
             raise ValueError(f"expected sample [B, {self.cfg.in_channels}, H, W], got {tuple(sample.shape)}")
         scale = float((cross_attention_kwargs or {}).get("scale", 1.0))
         self._sync_engine_lora(scale)
-        custom = {p: a for p, a in self._attn.items() if not isinstance(a.processor, B200AttnProcessor)}
-        eps = self.engine.forward(sample, timestep, class_labels, attn_overrides=custom or None, lora_scale=scale)
+        eps = self.engine.forward(sample, timestep, class_labels, attn_overrides=self.custom_attn_processors(),
+                                  lora_scale=scale)
         eps = eps.to(sample.dtype)
         return UNet2DConditionOutput(sample=eps) if return_dict else (eps,)
 

@@ -30,6 +30,13 @@ class PackedWeight:
     c1: int = 0
     c2: int = 0
     geglu: bool = False
+    alg_macs_per_row: Optional[float] = None   # algorithmic (unpadded) N*K of the layer; default: stored N*K
+
+    @property
+    def macs_per_row(self) -> float:
+        if self.alg_macs_per_row is not None:
+            return self.alg_macs_per_row
+        return float(self.n_valid * (2 if self.geglu else 1) * self.k)
 
     @property
     def n_pad(self) -> int:
@@ -90,9 +97,14 @@ def conv_gemm(pw: PackedWeight, a0: Tensor, nb: int, h: int, w: int, out: Tensor
     if residual is not None:
         assert residual.dtype == torch.bfloat16
         res_ld = pw.n_valid
+    info = None
+    if _lib.PROFILE is not None:
+        m_out = nb * h * w if stride == 1 else nb * ((h - 1) // 2 + 1) * ((w - 1) // 2 + 1)
+        info = {"flops": 2.0 * m_out * pw.macs_per_row, "m": nb * h * w, "n": pw.n_valid,
+                "k": pw.k, "bn": pw.block_n, "taps": pw.ntaps}
     call("b200_conv_gemm", ptr(a0), pw.c0, ptr(a1) if pw.c1 else None, pw.c1, ptr(a2) if pw.c2 else None, pw.c2,
          nb, h, w, pw.ntaps, stride, ptr(pw.w), pw.n_pad, pw.n_valid, ptr(pw.bias), ptr(rowvec), rowvec_ld,
-         ptr(residual), res_ld, ptr(out), ld, int(out_fp32), int(pw.geglu), pw.block_n, max_ctas, stream())
+         ptr(residual), res_ld, ptr(out), ld, int(out_fp32), int(pw.geglu), pw.block_n, max_ctas, stream(), info=info)
     return out
 
 
@@ -122,7 +134,8 @@ def attention(qkv: Tensor, out: Tensor, batch: int, seq: int, heads: int, head_d
     assert qkv.numel() == batch * seq * 3 * heads * head_dim
     if scale is None:
         scale = head_dim ** -0.5
-    call("b200_attention", ptr(qkv), ptr(out), batch, seq, heads, head_dim, float(scale), variant, stream())
+    info = {"flops": 4.0 * batch * heads * seq * seq * head_dim} if _lib.PROFILE is not None else None
+    call("b200_attention", ptr(qkv), ptr(out), batch, seq, heads, head_dim, float(scale), variant, stream(), info=info)
     return out
 
 
