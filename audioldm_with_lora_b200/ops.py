@@ -117,14 +117,16 @@ def groupnorm_silu(x0: Tensor, c0: int, x1: Optional[Tensor], c1: int, nb: int, 
     assert x0.dtype == torch.bfloat16 and y.dtype == torch.bfloat16 and partial.dtype == torch.float32
     assert partial.numel() >= gn_partial_floats(nb, hw, groups)
     assert gamma.numel() == c0 + c1 and gamma.dtype == torch.float32
+    info = {"desc": f"nb{nb} hw{hw} c{c0}+{c1}", "bytes": 4.0 * nb * hw * (c0 + c1)} if _lib.PROFILE is not None else None
     call("b200_groupnorm_silu", ptr(x0), c0, ptr(x1) if c1 else None, c1, nb, hw, groups, ptr(gamma), ptr(beta),
-         float(eps), int(silu), ptr(partial), ptr(y), stream())
+         float(eps), int(silu), ptr(partial), ptr(y), stream(), info=info)
     return y
 
 
 def layernorm(x: Tensor, m: int, c: int, gamma: Tensor, beta: Tensor, eps: float, y: Tensor) -> Tensor:
     assert x.dtype == torch.bfloat16 and y.dtype == torch.bfloat16
-    call("b200_layernorm", ptr(x), m, c, ptr(gamma), ptr(beta), float(eps), ptr(y), stream())
+    info = {"desc": f"m{m} c{c}", "bytes": 4.0 * m * c} if _lib.PROFILE is not None else None
+    call("b200_layernorm", ptr(x), m, c, ptr(gamma), ptr(beta), float(eps), ptr(y), stream(), info=info)
     return y
 
 
@@ -134,7 +136,8 @@ def attention(qkv: Tensor, out: Tensor, batch: int, seq: int, heads: int, head_d
     assert qkv.numel() == batch * seq * 3 * heads * head_dim
     if scale is None:
         scale = head_dim ** -0.5
-    info = {"flops": 4.0 * batch * heads * seq * seq * head_dim} if _lib.PROFILE is not None else None
+    info = ({"flops": 4.0 * batch * heads * seq * seq * head_dim, "desc": f"b{batch} s{seq} d{head_dim}"}
+            if _lib.PROFILE is not None else None)
     call("b200_attention", ptr(qkv), ptr(out), batch, seq, heads, head_dim, float(scale), variant, stream(), info=info)
     return out
 

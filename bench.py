@@ -165,7 +165,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ddim-steps", type=int, default=STEPS_DDIM,
+                    help="denoising steps per clip (default 200 = the BASELINE config; smaller only for ncu launch lists)")
     args = ap.parse_args()
+    if args.ddim_steps != STEPS_DDIM:
+        globals()["STEPS_DDIM"] = args.ddim_steps
+        CONFIG["ddim_steps"] = args.ddim_steps
+        CONFIG["workload"] += f" [NOT THE BASELINE CONFIG: {args.ddim_steps} DDIM steps]"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -306,7 +312,7 @@ def main():
                                     "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["flops"] and v["ms"] else None}
                                 for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])},
     }
-    if world == 1:
+    if world == 1 and STEPS_DDIM >= 8:
         cb = cpu_reference_arm(4, 1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
