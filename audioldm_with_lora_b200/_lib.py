@@ -31,9 +31,8 @@ _PROTOS = {
     "b200_conv_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                c_int, c_int, c_int, c_int, c_void_p]),
-    "b200_gn_nslab": (c_int, [c_int]),
     "b200_groupnorm_silu": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
-                                    c_int, c_void_p, c_void_p, c_void_p]),
+                                    c_int, c_void_p, c_void_p]),
     "b200_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     "b200_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "b200_time_class_embed": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
@@ -100,4 +99,4 @@ def call(name: str, *args, info=None) -> None:
     if PROFILE is not None:
         e1.record()
         PROFILE.append((name, e0, e1, info))
-    launch_count += 2 if name == "b200_groupnorm_silu" else 1
+    launch_count += 1

@@ -101,6 +101,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t t_s = tmem_base;               // S: columns [0, 128)
   const uint32_t t_o = tmem_base + 128;         // O_blk: columns [128, 128 + D)
 
@@ -278,8 +280,7 @@ static int launch_attention(const CUtensorMap& tm, AttnParams& p, cudaStream_t s
     configured = true;
   }
   dim3 grid((p.seq + kQ - 1) / kQ, p.batch * p.heads);
-  attention_kernel<D><<<grid, kAttnThreads, smem_bytes, stream>>>(tm, p);
-  B200_CHECK_LAUNCH("attention");
+  B200_CHECK_PDL("attention", launch_pdl(attention_kernel<D>, grid, dim3(kAttnThreads), (size_t)smem_bytes, stream, 0, tm, p));
   return B200_OK;
 }
 

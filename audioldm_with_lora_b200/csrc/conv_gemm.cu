@@ -12,8 +12,13 @@
 // * tcgen05.mma (UMMA 128 x block_n x 16, bf16 -> fp32 in TMEM), 128B-swizzled K-major smem
 //   tiles, mbarrier ring, persistent CTAs, double-buffered TMEM accumulator so the epilogue of
 //   tile i overlaps the mainloop of tile i+1.
-// * Epilogue (4 warps, one accumulator row per thread): + bias[n] + per-image row vector
-//   (timestep/class embedding projection, K6) + residual, optional GEGLU (K3), bf16/fp32 store.
+// * Epilogue: 8 warps (two per TMEM lane quarter, alternating 64-column chunks), one accumulator
+//   row per thread: + bias[n] + per-image row vector (timestep/class embedding projection, K6)
+//   + residual, optional GEGLU (K3).  bf16 results are staged in a per-warp 128B-swizzled smem
+//   tile and written with TMA stores (coalesced, asynchronous, tails clipped by the tensor map);
+//   fp32 / stride-2 outputs use direct 16-byte stores.
+// * Programmatic dependent launch: the prologue (barrier init, TMEM alloc, descriptor prefetch)
+//   overlaps the tail of the previous kernel in the stream / CUDA graph.
 //
 // Replaces (reference call sites -> diffusers/torch): F.conv2d / F.linear under
 // UNet2DConditionModel.forward, /root/reference/script/train/train_audioldm_lora.py:539-546.
@@ -25,7 +30,10 @@ namespace b200 {
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;              // 64 bf16 = one 128B swizzle row
 static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
-static constexpr int kThreads = 192;            // warp0 TMA, warp1 MMA, warps2-5 epilogue
+static constexpr int kEpiWarps = 8;
+static constexpr int kThreads = 64 + kEpiWarps * 32;    // warp0 TMA, warp1 MMA, warps2-9 epilogue
+static constexpr int kEpiStageBytes = 32 * 128;         // per-warp staging: 32 rows x 64 bf16
+static constexpr int kSmemLimit = 227 * 1024;
 
 struct ConvGemmParams {
   int seg_end0, seg_end1, num_kb;   // k-block boundaries of the segments
@@ -48,19 +56,39 @@ struct ConvGemmParams {
   int tmem_cols;
   int stride;                       // 1, or 2: keep even (h, w) only (Downsample2D: k3 s2 p1)
   int Hout, Wout;
+  int tma_out;                      // 1: bf16 stride-1 output through smem staging + TMA store
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact-erf GELU to ~2e-7 absolute (Abramowitz-Stegun 7.1.26 erfc; bf16 output rounding is 4e-3 relative):
+//   gelu(g) = g/2 (1 + erf(g/sqrt2));  erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1/(1 + p z)
+__device__ __forceinline__ float gelu_erf(float g) {
+  const float z = fabsf(g) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = poly * t * __expf(-z * z);
+  return g >= 0.f ? g * fmaf(-0.5f, e, 1.0f) : 0.5f * g * e;
+}
+
+__device__ __forceinline__ void add8(float (&v)[8], const float* src) {
+  const float4 b0 = *reinterpret_cast<const float4*>(src);
+  const float4 b1 = *reinterpret_cast<const float4*>(src + 4);
+  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
-                 const ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmOut, const ConvGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024B alignment for the 128B swizzle atoms.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = kABytes + p.block_n * kBlockK * 2;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint8_t* epi_smem = smem + p.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * kEpiStageBytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -73,13 +101,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB);
+    if (p.tma_out) tma_prefetch_desc(&tmOut);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 128);
+      mbar_init(&tempty_bar[b], kEpiWarps * 32);
     }
     fence_barrier_init();
   }
@@ -91,6 +120,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above overlapped the previous kernel's tail; from here on we touch its outputs.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ================================================================ TMA producer
@@ -167,18 +199,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   } else {
     // ================================================================ epilogue warps
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int hf = (warp - 2) >> 2;         // which of the two warps of the quarter: takes chunks cc % 2 == hf
     const int row = q * 32 + lane;          // accumulator row == tile pixel
     const int wl = row % p.W;
     const int hl = (row / p.W) % p.BH;
     const int nl = row / (p.W * p.BH);
+    // TMA-store box of this warp's 32 rows inside the tile (w fastest, then h, then image)
+    const int q_w = (q * 32) % p.W;
+    const int q_h = ((q * 32) / p.W) % p.BH;
+    const int q_n = (q * 32) / (p.W * p.BH);
+    uint8_t* stage = epi_smem + (warp - 2) * kEpiStageBytes;
+    const uint32_t stage_row = smem_u32(stage) + lane * 128;
+    const int half = p.block_n / 2;
+    const int out_cols = p.geglu ? half : p.block_n;     // output columns per tile
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t use = it >> 1;
       const int n_tile = t % p.num_n_tiles;
       const int m_tile = t / p.num_n_tiles;
-      const int h = (m_tile % p.tiles_h) * p.BH + hl;
-      const int n = (m_tile / p.tiles_h) * p.BNI + nl;
+      const int h_t = (m_tile % p.tiles_h) * p.BH;
+      const int n_t = (m_tile / p.tiles_h) * p.BNI;
+      const int h = h_t + hl;
+      const int n = n_t + nl;
       bool row_ok = (h < p.H) && (n < p.NB);
       size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + wl;
       if (p.stride == 2) {
@@ -189,9 +232,84 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * p.block_n;
 
-      if (!p.geglu) {
+      if (p.tma_out) {
+        // -------- bf16, stride 1: 64-column chunks -> swizzled smem -> TMA store
+        const int nchunks = out_cols >> 6;
+        for (int cc = hf; cc < nchunks; cc += 2) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int oc = cc * 64 + hh * 32;              // output column inside the tile
+            const int gcol = n_tile * out_cols + oc;       // global output column
+            uint32_t r[32];
+            if (!p.geglu) {
+              tmem_ld_x32(t_row + oc, r);
+              tmem_wait_ld();
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+                const int cg = gcol + g * 8;
+                if (p.bias) add8(v, p.bias + cg);
+                if (row_ok && cg < p.n_valid) {
+                  if (p.rowvec) add8(v, p.rowvec + static_cast<size_t>(n) * p.rowvec_ld + cg);
+                  if (p.residual) {
+                    const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + pix * p.res_ld + cg);
+                    v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                    v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pk[hh * 16 + g * 4 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+              }
+            } else {
+              // GEGLU: tile columns [0, bn/2) are values, [bn/2, bn) the matching gates.
+              uint32_t rg[32];
+              tmem_ld_x32(t_row + oc, r);
+              tmem_ld_x32(t_row + half + oc, rg);
+              tmem_wait_ld();
+              const int bcol = n_tile * p.block_n + oc;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float v[8], gt[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[j] = __uint_as_float(r[g * 8 + j]);
+                  gt[j] = __uint_as_float(rg[g * 8 + j]);
+                }
+                if (p.bias) {
+                  add8(v, p.bias + bcol + g * 8);
+                  add8(gt, p.bias + bcol + half + g * 8);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] *= gelu_erf(gt[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pk[hh * 16 + g * 4 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+              }
+            }
+          }
+          // the previous TMA store of this warp must have finished reading the staging tile
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t addr = stage_row + ((g ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
+                         "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmOut, stage, n_tile * out_cols + cc * 64, q_w, h_t + q_h, n_t + q_n);
+            tma_store_commit();
+          }
+        }
+      } else {
+        // -------- fp32 output and/or stride 2: direct 16-byte stores, 32-column groups
         const int col_base = n_tile * p.block_n;
-        for (int c = 0; c < p.block_n / 32; ++c) {
+        for (int c = hf; c < p.block_n / 32; c += 2) {
           uint32_t r[32];
           tmem_ld_x32(t_row + c * 32, r);
           tmem_wait_ld();
@@ -204,19 +322,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-                if (p.bias) {
-                  const float4 b0 = *reinterpret_cast<const float4*>(p.bias + cg);
-                  const float4 b1 = *reinterpret_cast<const float4*>(p.bias + cg + 4);
-                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                }
-                if (p.rowvec) {
-                  const float* rv = p.rowvec + static_cast<size_t>(n) * p.rowvec_ld + cg;
-                  const float4 b0 = *reinterpret_cast<const float4*>(rv);
-                  const float4 b1 = *reinterpret_cast<const float4*>(rv + 4);
-                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                }
+                if (p.bias) add8(v, p.bias + cg);
+                if (p.rowvec) add8(v, p.rowvec + static_cast<size_t>(n) * p.rowvec_ld + cg);
                 if (p.residual) {
                   const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + pix * p.res_ld + cg);
                   v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
@@ -237,45 +344,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
           }
         }
-      } else {
-        // GEGLU: tile columns [0, bn/2) are values, [bn/2, bn) the matching gates.
-        const int half = p.block_n / 2;
-        const int out_base = n_tile * half;
-        for (int c = 0; c < half / 32; ++c) {
-          uint32_t rv[32], rg[32];
-          tmem_ld_x32(t_row + c * 32, rv);
-          tmem_ld_x32(t_row + half + c * 32, rg);
-          tmem_wait_ld();
-          if (row_ok) {
-            const int bcol = n_tile * p.block_n + c * 32;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int oc = out_base + c * 32 + g * 8;
-              if (oc < p.n_valid) {
-                float o8[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float val = __uint_as_float(rv[g * 8 + j]);
-                  float gate = __uint_as_float(rg[g * 8 + j]);
-                  if (p.bias) {
-                    val += p.bias[bcol + g * 8 + j];
-                    gate += p.bias[bcol + half + g * 8 + j];
-                  }
-                  o8[j] = val * gelu_erf(gate);
-                }
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + oc;
-                uint4 pk;
-                pk.x = pack_bf16x2(o8[0], o8[1]); pk.y = pack_bf16x2(o8[2], o8[3]);
-                pk.z = pack_bf16x2(o8[4], o8[5]); pk.w = pack_bf16x2(o8[6], o8[7]);
-                *reinterpret_cast<uint4*>(o) = pk;
-              }
-            }
-          }
-        }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[buf]);
     }
+    if (p.tma_out && lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -321,8 +394,9 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
   B200_CHECK_ARG(block_n >= 32 && block_n <= 256 && block_n % 32 == 0, "conv_gemm: block_n %d unsupported", block_n);
   B200_CHECK_ARG(n_pad % block_n == 0, "conv_gemm: n_pad %d not a multiple of block_n %d", n_pad, block_n);
   B200_CHECK_ARG(n_valid % 8 == 0 && n_valid <= (geglu ? n_pad / 2 : n_pad), "conv_gemm: n_valid %d invalid", n_valid);
-  B200_CHECK_ARG(!geglu || (block_n % 64 == 0 && !out_fp32 && !residual && !rowvec), "conv_gemm: geglu constraints");
+  B200_CHECK_ARG(!geglu || (block_n % 128 == 0 && !out_fp32 && !residual && !rowvec && stride == 1), "conv_gemm: geglu constraints");
   B200_CHECK_ARG(nb > 0 && h > 0 && w > 0, "conv_gemm: empty activation");
+  B200_CHECK_ARG(out_ld % 8 == 0, "conv_gemm: out_ld %d must be a multiple of 8", out_ld);
 
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
@@ -344,16 +418,17 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
   p.bias = bias; p.rowvec = rowvec; p.rowvec_ld = rowvec_ld;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.res_ld = res_ld;
   p.out = out; p.out_ld = out_ld; p.out_fp32 = out_fp32; p.geglu = geglu;
+  p.tma_out = (!out_fp32 && stride == 1 && block_n % 64 == 0) ? 1 : 0;
   int tc = 32;
   while (tc < 2 * block_n) tc *= 2;
   p.tmem_cols = tc;
   const int stage_bytes = kABytes + block_n * kBlockK * 2;
-  const int smem_budget = 200 * 1024;
-  p.stages = smem_budget / stage_bytes;
+  const int fixed = kEpiWarps * kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  p.stages = (kSmemLimit - fixed) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
-  const int smem_bytes = p.stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  const int smem_bytes = p.stages * stage_bytes + fixed;
 
-  CUtensorMap tA[3], tB;
+  CUtensorMap tA[3], tB, tO;
   const void* srcs[3] = {a0, a1 ? a1 : a0, a2 ? a2 : a0};
   const int chans[3] = {c0, c1 ? c1 : c0, c2 ? c2 : c0};
   for (int i = 0; i < 3; ++i) {
@@ -372,18 +447,33 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
     int rc = make_tmap_bf16(&tB, wpacked, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
+  if (p.tma_out) {
+    // each epilogue warp stores its 32 accumulator rows x 64 columns: box = (64, bw, bh, bn), w fastest
+    const int bw = w < 32 ? w : 32;
+    int bh = 32 / bw;
+    if (bh > p.BH) bh = p.BH;
+    const int bn = 32 / (bw * bh);
+    const uint64_t L = out_ld;
+    uint64_t dims[4] = {(uint64_t)n_valid, (uint64_t)w, (uint64_t)h, (uint64_t)nb};
+    uint64_t strides[3] = {L, L * w, L * w * h};
+    uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+    int rc = make_tmap_bf16(&tO, out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  } else {
+    tO = tB;
+  }
 
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   }
   int grid = p.num_m_tiles * p.num_n_tiles;
   int cap = max_ctas > 0 ? max_ctas : num_sms;
   if (grid > cap) grid = cap;
-  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tA[0], tA[1], tA[2], tB, p);
-  B200_CHECK_LAUNCH("conv_gemm");
+  B200_CHECK_PDL("conv_gemm", launch_pdl(conv_gemm_kernel, dim3(grid), dim3(kThreads), (size_t)smem_bytes, stream, 0,
+                                         tA[0], tA[1], tA[2], tB, tO, p));
   return B200_OK;
 }

@@ -77,4 +77,40 @@ inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint
   return B200_OK;
 }
 
+
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel may start while its
+// predecessor in the stream drains; kernels call pdl_wait() before touching dependent global memory.
+// Captured into CUDA graphs as programmatic dependency edges.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
+  if (cluster_x > 0) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define B200_CHECK_PDL(name, expr)                                                                     \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return ::b200::fail(::b200::B200_ERR_CUDA, "%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
 }  // namespace b200

@@ -1,158 +1,182 @@
-// GroupNorm (+SiLU) and LayerNorm for NHWC bf16 activations -- HBM-bound, vectorised 16 B accesses.
+// GroupNorm (+SiLU) and LayerNorm for NHWC bf16 activations -- HBM/L2-bound, vectorised 16 B accesses.
 //
-// GroupNorm is two launches: gn_stats writes per-(image, slab, group) partial sum / sum-of-squares
-// (deterministic: no atomics, no memset), gn_apply reduces the partials for its image in shared
-// memory, then normalises, applies the affine and optional SiLU, and writes bf16.  Both read up to
-// two source tensors so the up-block `torch.cat([h, skip], 1)` is consumed in place (K11).
-// Statistics are fp32 whatever the storage type.
+// GroupNorm is ONE launch: a thread-block cluster (up to 8 CTAs, distributed shared memory) owns one
+// image.  Pass 1: every CTA streams its slab of pixels, each thread keeping fp32 sum / sum-of-squares
+// of a fixed 8-channel vector in registers; fixed-order reductions (no atomics => bit-deterministic)
+// give per-group partials, which the CTAs of the cluster exchange through DSMEM.  Pass 2 re-reads the
+// slab (an L2 hit: the producing conv just wrote it), normalises, applies the affine and optional
+// SiLU, and writes bf16.  Both passes read up to two source tensors so the up-block
+// `torch.cat([h, skip], 1)` is consumed in place (K11).  Statistics are fp32 whatever the storage type.
 //
 // Replaces F.group_norm + F.silu in ResnetBlock2D / Transformer2DModel / conv_norm_out and
 // F.layer_norm in BasicTransformerBlock (diffusers, driven from
 // /root/reference/script/train/train_audioldm_lora.py:539-546).
+#include <cooperative_groups.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace b200 {
 
-static constexpr int kGnThreads = 256;
+static constexpr int kGnThreads = 512;
 static constexpr int kMaxC = 2560;          // cat(1280, 1280) at AudioLDM-L
+static constexpr int kGnUnroll = 4;
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
   f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
 }
 
-// x0 [NB, HW, C0], x1 [NB, HW, C1] (nullable) ; partial [NB, nslab, groups, 2]
-__global__ void __launch_bounds__(kGnThreads)
-gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int C0, const __nv_bfloat16* __restrict__ x1, int C1, int HW,
-                int groups, int nslab, float* __restrict__ partial) {
-  const int C = C0 + C1;
-  const int vec_per_pix = C / 8;
-  const int n = blockIdx.y;
-  const int slab = blockIdx.x;
-  const int pix_per_slab = (HW + nslab - 1) / nslab;
-  const int p_begin = slab * pix_per_slab;
-  const int p_end = min(HW, p_begin + pix_per_slab);
-  __shared__ float s_sum[kMaxC];
-  __shared__ float s_sq[kMaxC];
-  for (int c = threadIdx.x; c < C; c += kGnThreads) {
-    s_sum[c] = 0.f;
-    s_sq[c] = 0.f;
-  }
-  __syncthreads();
-  // thread -> fixed channel vector, strided over pixels
-  const int total_vec = (p_end - p_begin) * vec_per_pix;
-  if (vec_per_pix <= kGnThreads) {
-    const int v = threadIdx.x % vec_per_pix;
-    const int pl = threadIdx.x / vec_per_pix;
-    const int pstride = kGnThreads / vec_per_pix;       // whole pixel lanes; leftover threads idle
-    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int c = v * 8;
-    const __nv_bfloat16* src = (c < C0) ? x0 + (static_cast<size_t>(n) * HW) * C0 + c
-                                        : x1 + (static_cast<size_t>(n) * HW) * C1 + (c - C0);
-    const int ld = (c < C0) ? C0 : C1;
-    for (int p = p_begin + pl; pl < pstride && p < p_end; p += pstride) {
-      const uint4 u = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(p) * ld);
-      float f[8];
-      unpack8(u, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a[j] += f[j];
-        b[j] += f[j] * f[j];
-      }
-    }
-    if (pl < pstride) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&s_sum[c + j], a[j]);
-        atomicAdd(&s_sq[c + j], b[j]);
-      }
-    }
-  } else {
-    for (int i = threadIdx.x; i < total_vec; i += kGnThreads) {
-      const int p = p_begin + i / vec_per_pix;
-      const int c = (i % vec_per_pix) * 8;
-      const __nv_bfloat16* src = (c < C0) ? x0 + (static_cast<size_t>(n) * HW + p) * C0 + c
-                                          : x1 + (static_cast<size_t>(n) * HW + p) * C1 + (c - C0);
-      const uint4 u = *reinterpret_cast<const uint4*>(src);
-      float f[8];
-      unpack8(u, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&s_sum[c + j], f[j]);
-        atomicAdd(&s_sq[c + j], f[j] * f[j]);
-      }
-    }
-  }
-  __syncthreads();
-  const int cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += kGnThreads) {
-    float s = 0.f, q = 0.f;
-    for (int j = 0; j < cpg; ++j) {
-      s += s_sum[g * cpg + j];
-      q += s_sq[g * cpg + j];
-    }
-    float* dst = partial + ((static_cast<size_t>(n) * nslab + slab) * groups + g) * 2;
-    dst[0] = s;
-    dst[1] = q;
-  }
-}
+struct GnParams {
+  const __nv_bfloat16* x0;
+  const __nv_bfloat16* x1;
+  int C0, C1, HW, groups;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int silu;
+  __nv_bfloat16* y;
+};
 
-// y [NB, HW, C] = act( (x - mean) * rstd * gamma + beta )
+// grid (cluster_size, NB), cluster (cluster_size, 1, 1): blockIdx.x = rank of the CTA in its image's cluster.
 __global__ void __launch_bounds__(kGnThreads)
-gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int C0, const __nv_bfloat16* __restrict__ x1, int C1, int HW,
-                int groups, int nslab, const float* __restrict__ partial, const float* __restrict__ gamma,
-                const float* __restrict__ beta, float eps, int silu, __nv_bfloat16* __restrict__ y, int pix_per_block) {
-  const int C = C0 + C1;
+groupnorm_silu_kernel(const GnParams p) {
+  cg::cluster_group cluster = cg::this_cluster();
+  pdl_launch_dependents();
+  pdl_wait();
+  const int nrank = gridDim.x;
+  const int rank = blockIdx.x;
   const int n = blockIdx.y;
-  __shared__ float s_scale[kMaxC];
-  __shared__ float s_shift[kMaxC];
+  const int C = p.C0 + p.C1;
+  const int vpp = C >> 3;                           // 16-byte vectors per pixel
+  const int nlanes = kGnThreads / vpp;              // pixel lanes per CTA (>= 1: C <= 2560)
+  const int tid = threadIdx.x;
+  const bool active = tid < nlanes * vpp;
+  const int v = tid % vpp;
+  const int lane = tid / vpp;
+  const int c = v * 8;
+  const int cpg = C / p.groups;
+
+  __shared__ float s_sum[kGnThreads * 8];           // [lane][C]
+  __shared__ float s_sq[kGnThreads * 8];
+  __shared__ float s_gpart[128];                    // this CTA's per-group {sum, sumsq}; read by cluster peers
   __shared__ float s_mean[64], s_rstd[64];
-  const int cpg = C / groups;
-  if (threadIdx.x < groups) {
-    float s = 0.f, q = 0.f;
-    for (int k = 0; k < nslab; ++k) {
-      const float* src = partial + ((static_cast<size_t>(n) * nslab + k) * groups + threadIdx.x) * 2;
-      s += src[0];
-      q += src[1];
+
+  const int pps = (p.HW + nrank - 1) / nrank;
+  const int p_begin = rank * pps;
+  const int p_end = min(p.HW, p_begin + pps);
+  const bool from0 = c < p.C0;
+  const int ld = from0 ? p.C0 : p.C1;
+  const __nv_bfloat16* src = from0 ? p.x0 + static_cast<size_t>(n) * p.HW * p.C0 + c
+                                   : p.x1 + static_cast<size_t>(n) * p.HW * p.C1 + (c - p.C0);
+
+  // ---- pass 1: per-thread channel sums over this CTA's slab
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  if (active) {
+    for (int px = p_begin + lane; px < p_end; px += nlanes * kGnUnroll) {
+      uint4 u[kGnUnroll];
+#pragma unroll
+      for (int k = 0; k < kGnUnroll; ++k) {
+        const int pk = px + k * nlanes;
+        u[k] = (pk < p_end) ? *reinterpret_cast<const uint4*>(src + static_cast<size_t>(pk) * ld) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int k = 0; k < kGnUnroll; ++k) {
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a[j] += f[j];
+          b[j] = fmaf(f[j], f[j], b[j]);
+        }
+      }
     }
-    const float cnt = static_cast<float>(HW) * cpg;
-    const float mean = s / cnt;
-    const float var = fmaxf(q / cnt - mean * mean, 0.f);
-    s_mean[threadIdx.x] = mean;
-    s_rstd[threadIdx.x] = rsqrtf(var + eps);
+    float* ds = s_sum + lane * C + c;
+    float* dq = s_sq + lane * C + c;
+    *reinterpret_cast<float4*>(ds) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(ds + 4) = make_float4(a[4], a[5], a[6], a[7]);
+    *reinterpret_cast<float4*>(dq) = make_float4(b[0], b[1], b[2], b[3]);
+    *reinterpret_cast<float4*>(dq + 4) = make_float4(b[4], b[5], b[6], b[7]);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += kGnThreads) {
-    const int g = c / cpg;
-    const float sc = gamma[c] * s_rstd[g];
-    s_scale[c] = sc;
-    s_shift[c] = beta[c] - s_mean[g] * sc;
+  // lanes -> per-channel totals (fixed order), kept in lane 0's row
+  for (int ch = tid; ch < C; ch += kGnThreads) {
+    float s = 0.f, q = 0.f;
+    for (int l = 0; l < nlanes; ++l) {
+      s += s_sum[l * C + ch];
+      q += s_sq[l * C + ch];
+    }
+    s_sum[ch] = s;
+    s_sq[ch] = q;
   }
   __syncthreads();
-  const int vec_per_pix = C / 8;
-  const int p_begin = blockIdx.x * pix_per_block;
-  const int p_end = min(HW, p_begin + pix_per_block);
-  const int total_vec = (p_end - p_begin) * vec_per_pix;
-  for (int i = threadIdx.x; i < total_vec; i += kGnThreads) {
-    const int p = p_begin + i / vec_per_pix;
-    const int c = (i % vec_per_pix) * 8;
-    const __nv_bfloat16* src = (c < C0) ? x0 + (static_cast<size_t>(n) * HW + p) * C0 + c
-                                        : x1 + (static_cast<size_t>(n) * HW + p) * C1 + (c - C0);
-    const uint4 u = *reinterpret_cast<const uint4*>(src);
-    float f[8];
-    unpack8(u, f);
+  if (tid < 2 * p.groups) {
+    const int g = tid >> 1;
+    const float* srcv = (tid & 1) ? s_sq : s_sum;
+    float s = 0.f;
+    for (int j = 0; j < cpg; ++j) s += srcv[g * cpg + j];
+    s_gpart[tid] = s;
+  }
+  cluster.sync();
+  // ---- cluster exchange through DSMEM (fixed rank order)
+  if (tid < 2 * p.groups) {
+    float s = 0.f;
+    for (int r = 0; r < nrank; ++r) s += cluster.map_shared_rank(s_gpart, r)[tid];
+    s_gpart[64 + tid] = s;                          // local copy of the totals (peers read [0, 64) only)
+  }
+  __syncthreads();
+  cluster.barrier_arrive();                         // peers may exit once everyone has read their partials
+  if (tid < p.groups) {
+    const float cnt = static_cast<float>(p.HW) * cpg;
+    const float mean = s_gpart[64 + 2 * tid] / cnt;
+    const float var = fmaxf(s_gpart[64 + 2 * tid + 1] / cnt - mean * mean, 0.f);
+    s_mean[tid] = mean;
+    s_rstd[tid] = rsqrtf(var + p.eps);
+  }
+  __syncthreads();
+
+  // ---- pass 2: normalise + affine (+ SiLU)
+  if (active) {
+    float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float v = f[j] * s_scale[c + j] + s_shift[c + j];
-      if (silu) v = v / (1.0f + __expf(-v));
-      f[j] = v;
+      const int g = (c + j) / cpg;
+      sc[j] = p.gamma[c + j] * s_rstd[g];
+      sh[j] = p.beta[c + j] - s_mean[g] * sc[j];
     }
-    uint4 o;
-    o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-    o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(y + (static_cast<size_t>(n) * HW + p) * C + c) = o;
+    __nv_bfloat16* dst = p.y + static_cast<size_t>(n) * p.HW * C + c;
+    for (int px = p_begin + lane; px < p_end; px += nlanes * kGnUnroll) {
+      uint4 u[kGnUnroll];
+#pragma unroll
+      for (int k = 0; k < kGnUnroll; ++k) {
+        const int pk = px + k * nlanes;
+        u[k] = (pk < p_end) ? *reinterpret_cast<const uint4*>(src + static_cast<size_t>(pk) * ld) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int k = 0; k < kGnUnroll; ++k) {
+        const int pk = px + k * nlanes;
+        if (pk < p_end) {
+          float f[8];
+          unpack8(u[k], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float val = fmaf(f[j], sc[j], sh[j]);
+            if (p.silu) val = __fdividef(val, 1.0f + __expf(-val));
+            f[j] = val;
+          }
+          uint4 o;
+          o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+          o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(dst + static_cast<size_t>(pk) * C) = o;
+        }
+      }
+    }
   }
+  cluster.barrier_wait();
 }
 
 // One warp per row; C % 8 == 0, C <= 1280.  y = (x - mean) * rstd * gamma + beta  (eps inside sqrt)
@@ -162,6 +186,8 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int M, int C, const float*
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (warp >= M) return;
   const int nvec = C / 8;
   const __nv_bfloat16* row = x + static_cast<size_t>(warp) * C;
@@ -221,38 +247,23 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int M, int C, const float*
 
 using namespace b200;
 
-extern "C" int b200_gn_nslab(int hw) {
-  int nslab = hw / 128;
-  if (nslab < 1) nslab = 1;
-  if (nslab > 32) nslab = 32;
-  return nslab;
-}
-
-// partial must hold nb * b200_gn_nslab(hw) * groups * 2 floats.
 extern "C" int b200_groupnorm_silu(const void* x0, int c0, const void* x1, int c1, int nb, int hw, int groups,
-                                   const float* gamma, const float* beta, float eps, int silu, float* partial,
-                                   void* y, void* stream_v) {
+                                   const float* gamma, const float* beta, float eps, int silu, void* y,
+                                   void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const int C = c0 + c1;
-  B200_CHECK_ARG(x0 && y && partial && gamma && beta, "groupnorm: null pointer");
+  B200_CHECK_ARG(x0 && y && gamma && beta, "groupnorm: null pointer");
   B200_CHECK_ARG(c0 % 8 == 0 && c1 % 8 == 0 && C <= kMaxC, "groupnorm: channels (%d,%d) unsupported", c0, c1);
   B200_CHECK_ARG((c1 == 0) == (x1 == nullptr), "groupnorm: second source mismatch");
-  B200_CHECK_ARG(groups > 0 && groups <= 64 && C % groups == 0, "groupnorm: %d channels not divisible by %d groups", C, groups);
+  B200_CHECK_ARG(groups > 0 && groups <= 32 && C % groups == 0, "groupnorm: %d channels not divisible by %d groups", C, groups);
   B200_CHECK_ARG(nb > 0 && hw > 0, "groupnorm: empty input");
-  const int nslab = b200_gn_nslab(hw);
-  gn_stats_kernel<<<dim3(nslab, nb), kGnThreads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x0), c0,
-                                                             reinterpret_cast<const __nv_bfloat16*>(x1), c1, hw, groups,
-                                                             nslab, partial);
-  B200_CHECK_LAUNCH("gn_stats");
-  // ~16 KB of bf16 per block
-  int pix_per_block = (8192 + C - 1) / C;
-  if (pix_per_block < 1) pix_per_block = 1;
-  const int nblk = (hw + pix_per_block - 1) / pix_per_block;
-  gn_apply_kernel<<<dim3(nblk, nb), kGnThreads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x0), c0,
-                                                            reinterpret_cast<const __nv_bfloat16*>(x1), c1, hw, groups,
-                                                            nslab, partial, gamma, beta, eps, silu,
-                                                            reinterpret_cast<__nv_bfloat16*>(y), pix_per_block);
-  B200_CHECK_LAUNCH("gn_apply");
+  GnParams p;
+  p.x0 = reinterpret_cast<const __nv_bfloat16*>(x0); p.x1 = reinterpret_cast<const __nv_bfloat16*>(x1);
+  p.C0 = c0; p.C1 = c1; p.HW = hw; p.groups = groups; p.gamma = gamma; p.beta = beta; p.eps = eps; p.silu = silu;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  int cs = 8;
+  while (cs > 1 && hw < 4 * cs) cs >>= 1;           // at least 4 pixels per CTA of the cluster
+  B200_CHECK_PDL("groupnorm", launch_pdl(groupnorm_silu_kernel, dim3(cs, nb, 1), dim3(kGnThreads), 0, stream, cs, p));
   return B200_OK;
 }
 
@@ -264,8 +275,8 @@ extern "C" int b200_layernorm(const void* x, int m, int c, const float* gamma, c
   if (m == 0) return B200_OK;
   const int warps_per_block = 8;
   const int nblk = (m + warps_per_block - 1) / warps_per_block;
-  layernorm_kernel<<<nblk, warps_per_block * 32, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), m, c, gamma,
-                                                             beta, eps, reinterpret_cast<__nv_bfloat16*>(y));
-  B200_CHECK_LAUNCH("layernorm");
+  B200_CHECK_PDL("layernorm", launch_pdl(layernorm_kernel, dim3(nblk), dim3(warps_per_block * 32), 0, stream, 0,
+                                         reinterpret_cast<const __nv_bfloat16*>(x), m, c, gamma, beta, eps,
+                                         reinterpret_cast<__nv_bfloat16*>(y)));
   return B200_OK;
 }

@@ -26,6 +26,8 @@ sampler_step_kernel(const float* __restrict__ eps, float* __restrict__ x, float*
                     float* __restrict__ hist, const float* __restrict__ table, int* __restrict__ step_ptr,
                     float guidance, int do_cfg, int nb, int hw, int c, int c_pad,
                     __nv_bfloat16* __restrict__ xin_next, unsigned int* __restrict__ done_ctr) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int step = *step_ptr;
   const float* row = table + static_cast<size_t>(step) * 8;
   const float a = row[0], b = row[1];
@@ -94,62 +96,92 @@ sampler_step_kernel(const float* __restrict__ eps, float* __restrict__ x, float*
 }
 
 // ---------------------------------------------------------------------------------- embeddings
-// grid (nchunk, nb); block 256.  Every block recomputes the 1st MLP layer (tproj x ted MACs, tiny).
-__global__ void __launch_bounds__(256)
+// grid (nchunk, nb); block 256.  Weights arrive TRANSPOSED ([in, out] row-major) so that consecutive
+// threads read consecutive floats of one k-row: every load of the k loops is coalesced and independent
+// (no shuffles in the loop), i.e. the loops pipeline.  Every block recomputes the 1st MLP layer
+// (tproj x ted MACs, 256 KB of L2-resident weights); each block then produces kEmbCols of the 2*ted
+// outputs with a 4-way split of k across the thread block.
+static constexpr int kEmbThreads = 256;
+static constexpr int kEmbCols = 64;
+__global__ void __launch_bounds__(kEmbThreads)
 time_class_embed_kernel(const float* __restrict__ t_steps, const int* __restrict__ step_ptr, int per_sample,
                         const float* __restrict__ labels, int tproj, int ted, int class_in,
-                        const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                        const float* __restrict__ b2, const float* __restrict__ wc, const float* __restrict__ bc,
+                        const float* __restrict__ w1t, const float* __restrict__ b1, const float* __restrict__ w2t,
+                        const float* __restrict__ b2, const float* __restrict__ wct, const float* __restrict__ bc,
                         float* __restrict__ emb, __nv_bfloat16* __restrict__ silu_emb) {
   extern __shared__ float sm[];
   float* s_sin = sm;                  // [tproj]  ([cos | sin], flip_sin_to_cos=True)
   float* s_h = sm + tproj;            // [ted]
   float* s_lab = s_h + ted;           // [class_in]
+  float* s_red = s_lab + class_in;    // [4][kEmbCols]
+  pdl_launch_dependents();
+  pdl_wait();
   const int bidx = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  const float t = per_sample ? t_steps[bidx] : t_steps[step_ptr ? *step_ptr : 0];
-  const int half = tproj / 2;
-  for (int i = threadIdx.x; i < half; i += blockDim.x) {
-    const float freq = expf(-logf(10000.0f) * static_cast<float>(i) / static_cast<float>(half));
-    const float arg = t * freq;
-    s_sin[i] = cosf(arg);
-    s_sin[half + i] = sinf(arg);
-  }
-  for (int i = threadIdx.x; i < class_in; i += blockDim.x) s_lab[i] = labels[static_cast<size_t>(bidx) * class_in + i];
-  __syncthreads();
-  for (int o = warp; o < ted; o += nwarp) {
-    float acc = 0.f;
-    for (int k = lane; k < tproj; k += 32) acc += w1[static_cast<size_t>(o) * tproj + k] * s_sin[k];
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) {
-      const float v = acc + b1[o];
+  const int total = 2 * ted;
+  const int o_begin = blockIdx.x * kEmbCols;
+  if (o_begin >= total) return;
+  const bool time_half = o_begin < ted;         // ted % kEmbCols == 0: a block never straddles the halves
+  const int col = threadIdx.x % kEmbCols;
+  const int ks = threadIdx.x / kEmbCols;        // 0..3
+  float acc = 0.f;
+  if (time_half) {
+    const float t = per_sample ? t_steps[bidx] : t_steps[step_ptr ? *step_ptr : 0];
+    const int half = tproj / 2;
+    for (int i = threadIdx.x; i < half; i += kEmbThreads) {
+      const float freq = expf(-logf(10000.0f) * static_cast<float>(i) / static_cast<float>(half));
+      const float arg = t * freq;
+      s_sin[i] = cosf(arg);
+      s_sin[half + i] = sinf(arg);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < ted; o += kEmbThreads) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int k = 0;
+      for (; k + 3 < tproj; k += 4) {
+        a0 = fmaf(w1t[static_cast<size_t>(k) * ted + o], s_sin[k], a0);
+        a1 = fmaf(w1t[static_cast<size_t>(k + 1) * ted + o], s_sin[k + 1], a1);
+        a2 = fmaf(w1t[static_cast<size_t>(k + 2) * ted + o], s_sin[k + 2], a2);
+        a3 = fmaf(w1t[static_cast<size_t>(k + 3) * ted + o], s_sin[k + 3], a3);
+      }
+      for (; k < tproj; ++k) a0 = fmaf(w1t[static_cast<size_t>(k) * ted + o], s_sin[k], a0);
+      const float v = (a0 + a1) + (a2 + a3) + b1[o];
       s_h[o] = v / (1.0f + expf(-v));
     }
+    __syncthreads();
+    const int o = o_begin + col;
+    const int kper = (ted + 3) / 4;
+    const int k0 = ks * kper, k1 = min(ted, k0 + kper);
+    float a0 = 0.f, a1 = 0.f;
+    int k = k0;
+    for (; k + 1 < k1; k += 2) {
+      a0 = fmaf(w2t[static_cast<size_t>(k) * ted + o], s_h[k], a0);
+      a1 = fmaf(w2t[static_cast<size_t>(k + 1) * ted + o], s_h[k + 1], a1);
+    }
+    if (k < k1) a0 = fmaf(w2t[static_cast<size_t>(k) * ted + o], s_h[k], a0);
+    acc = a0 + a1;
+  } else {
+    for (int i = threadIdx.x; i < class_in; i += kEmbThreads) s_lab[i] = labels[static_cast<size_t>(bidx) * class_in + i];
+    __syncthreads();
+    const int o = o_begin - ted + col;
+    const int kper = (class_in + 3) / 4;
+    const int k0 = ks * kper, k1 = min(class_in, k0 + kper);
+    float a0 = 0.f, a1 = 0.f;
+    int k = k0;
+    for (; k + 1 < k1; k += 2) {
+      a0 = fmaf(wct[static_cast<size_t>(k) * ted + o], s_lab[k], a0);
+      a1 = fmaf(wct[static_cast<size_t>(k + 1) * ted + o], s_lab[k + 1], a1);
+    }
+    if (k < k1) a0 = fmaf(wct[static_cast<size_t>(k) * ted + o], s_lab[k], a0);
+    acc = a0 + a1;
   }
+  s_red[ks * kEmbCols + col] = acc;
   __syncthreads();
-  // this block's slice of the 2*ted outputs
-  const int total = 2 * ted;
-  const int per = (total + gridDim.x - 1) / gridDim.x;
-  const int o_begin = blockIdx.x * per, o_end = min(total, o_begin + per);
-  for (int o = o_begin + warp; o < o_end; o += nwarp) {
-    float acc = 0.f;
-    float bias;
-    if (o < ted) {
-      for (int k = lane; k < ted; k += 32) acc += w2[static_cast<size_t>(o) * ted + k] * s_h[k];
-      bias = b2[o];
-    } else {
-      const int oc = o - ted;
-      for (int k = lane; k < class_in; k += 32) acc += wc[static_cast<size_t>(oc) * class_in + k] * s_lab[k];
-      bias = bc[oc];
-    }
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) {
-      const float v = acc + bias;
-      if (emb) emb[static_cast<size_t>(bidx) * total + o] = v;
-      silu_emb[static_cast<size_t>(bidx) * total + o] = __float2bfloat16(v / (1.0f + expf(-v)));
-    }
+  if (threadIdx.x < kEmbCols) {
+    const int o = o_begin + col;
+    const float bias = time_half ? b2[o] : bc[o - ted];
+    const float v = ((s_red[col] + s_red[kEmbCols + col]) + (s_red[2 * kEmbCols + col] + s_red[3 * kEmbCols + col])) + bias;
+    if (emb) emb[static_cast<size_t>(bidx) * total + o] = v;
+    silu_emb[static_cast<size_t>(bidx) * total + o] = __float2bfloat16(v / (1.0f + expf(-v)));
   }
 }
 
@@ -174,6 +206,8 @@ __global__ void unpack_nhwc_to_nchw_kernel(const float* __restrict__ x, int nb, 
 // 16-byte vectors; src index = floor(dst * (in / out)) evaluated in fp32 like ATen's nearest kernel.
 __global__ void upsample_nearest_kernel(const uint4* __restrict__ x, int nb, int h, int w, int cv, int ho, int wo,
                                         uint4* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float sh = static_cast<float>(h) / static_cast<float>(ho);
   const float sw = static_cast<float>(w) / static_cast<float>(wo);
   const size_t total = static_cast<size_t>(nb) * ho * wo * cv;
@@ -267,25 +301,24 @@ extern "C" int b200_sampler_step(const float* eps, float* x, float* x_saved, flo
   unsigned int* ctr = nullptr;
   cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), g_sampler_done_ctr);
   const size_t npix = static_cast<size_t>(nb) * hw;
-  sampler_step_kernel<<<grid_for(npix, 256), 256, 0, stream>>>(eps, x, x_saved, hist, table, step_ptr, guidance, do_cfg,
-                                                              nb, hw, c, c_pad,
-                                                              reinterpret_cast<__nv_bfloat16*>(xin_next), ctr);
-  B200_CHECK_LAUNCH("sampler_step");
+  B200_CHECK_PDL("sampler_step", launch_pdl(sampler_step_kernel, dim3(grid_for(npix, 256)), dim3(256), 0, stream, 0, eps, x,
+                                            x_saved, hist, table, step_ptr, guidance, do_cfg, nb, hw, c, c_pad,
+                                            reinterpret_cast<__nv_bfloat16*>(xin_next), ctr));
   return B200_OK;
 }
 
 extern "C" int b200_time_class_embed(const float* t_steps, const int* step_ptr, int per_sample, const float* labels,
-                                     int nb, int tproj, int ted, int class_in, const float* w1, const float* b1,
-                                     const float* w2, const float* b2, const float* wc, const float* bc, float* emb,
+                                     int nb, int tproj, int ted, int class_in, const float* w1t, const float* b1,
+                                     const float* w2t, const float* b2, const float* wct, const float* bc, float* emb,
                                      void* silu_emb, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  B200_CHECK_ARG(t_steps && labels && w1 && b1 && w2 && b2 && wc && bc && silu_emb, "time_class_embed: null pointer");
-  B200_CHECK_ARG(nb > 0 && tproj % 2 == 0 && ted > 0 && class_in > 0, "time_class_embed: bad dims");
-  const size_t smem = sizeof(float) * (tproj + ted + class_in);
-  time_class_embed_kernel<<<dim3(16, nb), 256, smem, stream>>>(t_steps, step_ptr, per_sample, labels, tproj, ted,
-                                                               class_in, w1, b1, w2, b2, wc, bc, emb,
-                                                               reinterpret_cast<__nv_bfloat16*>(silu_emb));
-  B200_CHECK_LAUNCH("time_class_embed");
+  B200_CHECK_ARG(t_steps && labels && w1t && b1 && w2t && b2 && wct && bc && silu_emb, "time_class_embed: null pointer");
+  B200_CHECK_ARG(nb > 0 && tproj % 2 == 0 && ted > 0 && ted % kEmbCols == 0 && class_in > 0, "time_class_embed: bad dims");
+  const size_t smem = sizeof(float) * (tproj + ted + class_in + 4 * kEmbCols);
+  B200_CHECK_PDL("time_class_embed",
+                 launch_pdl(time_class_embed_kernel, dim3(2 * ted / kEmbCols, nb), dim3(kEmbThreads), smem, stream, 0,
+                            t_steps, step_ptr, per_sample, labels, tproj, ted, class_in, w1t, b1, w2t, b2, wct, bc, emb,
+                            reinterpret_cast<__nv_bfloat16*>(silu_emb)));
   return B200_OK;
 }
 
@@ -309,9 +342,9 @@ extern "C" int b200_upsample_nearest(const void* x, int nb, int h, int w, int c,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(x && y && nb > 0 && h > 0 && w > 0 && ho > 0 && wo > 0 && c % 8 == 0, "upsample_nearest: bad args");
   const size_t total = static_cast<size_t>(nb) * ho * wo * (c / 8);
-  upsample_nearest_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), nb, h, w, c / 8,
-                                                                   ho, wo, reinterpret_cast<uint4*>(y));
-  B200_CHECK_LAUNCH("upsample_nearest");
+  B200_CHECK_PDL("upsample_nearest", launch_pdl(upsample_nearest_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, 0,
+                                                reinterpret_cast<const uint4*>(x), nb, h, w, c / 8, ho, wo,
+                                                reinterpret_cast<uint4*>(y)));
   return B200_OK;
 }
 

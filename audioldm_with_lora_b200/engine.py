@@ -106,7 +106,7 @@ class UNetEngine:
     def _init_small(self) -> None:
         sd, S = self.sd, self._small
         for k in ("time_embedding.linear_1", "time_embedding.linear_2", "class_embedding"):
-            S[k + ".weight"] = self._dev(sd[k + ".weight"])
+            S[k + ".weight"] = self._dev(sd[k + ".weight"].t())          # [in, out]: coalesced in the embed kernel
             S[k + ".bias"] = self._dev(sd[k + ".bias"])
         for k, v in sd.items():
             if (".norm" in k or k.startswith("conv_norm_out")) and v.dim() == 1:
@@ -278,7 +278,6 @@ class UNetEngine:
 
         rowvec = ar.alloc((nb, plan["temb_total"]), torch.float32)
         ops.conv_gemm(W["temb"], silu_emb, 1, nb, 1, rowvec, out_ld=plan["temb_total"])
-        gn_part = ar.alloc((ops.gn_partial_floats(nb, sizes[0][0] * sizes[0][1]) + 64,), torch.float32)
 
         def tap(name, buf, lvl, c):
             if taps is not None:
@@ -289,7 +288,7 @@ class UNetEngine:
             hh, ww = sizes[lvl]
             y = ar.alloc((M(lvl), c0 + c1), bf16)
             return ops.groupnorm_silu(x0, c0, x1, c1, nb, hh * ww, S[name + ".weight"], S[name + ".bias"], eps, silu,
-                                      gn_part, y, cfg.groups)
+                                      y, cfg.groups)
 
         def conv(name, a0, lvl, *, a1=None, a2=None, rowvec_off=None, residual=None, stride=1, out=None,
                  out_lvl=None):
@@ -422,7 +421,7 @@ class UNetEngine:
         n = gn(hcur, cfg.block_out_channels[0], None, 0, 0, "conv_norm_out", 1e-5, True)
         ar.release(hcur)
         conv("conv_out", n, 0, out=eps_out)
-        ar.release(n); ar.release(rowvec); ar.release(gn_part)
+        ar.release(n); ar.release(rowvec)
         assert not ar.live, f"arena leak: {len(ar.live)} buffers"
         return eps_out
 

@@ -68,8 +68,8 @@ def num_m_tiles(nb: int, h: int, w: int) -> int:
 
 def choose_block_n(n: int, m_tiles: int, geglu: bool = False) -> int:
     """Tile width minimising (waves x per-tile cost) on 148 SMs; n is padded up to a multiple of it."""
-    best, best_cost = 32, None
-    step = 64 if geglu else 32
+    best, best_cost = 64, None
+    step = 128 if geglu else 64                 # the TMA-store epilogue works on 64-column output chunks
     for bn in range(step, 257, step):
         n_tiles = math.ceil(n / bn)
         waves = math.ceil(m_tiles * n_tiles / NUM_SMS)
@@ -108,18 +108,13 @@ def conv_gemm(pw: PackedWeight, a0: Tensor, nb: int, h: int, w: int, out: Tensor
     return out
 
 
-def gn_partial_floats(nb: int, hw: int, groups: int = 32) -> int:
-    return nb * _lib.load().b200_gn_nslab(hw) * groups * 2
-
-
 def groupnorm_silu(x0: Tensor, c0: int, x1: Optional[Tensor], c1: int, nb: int, hw: int, gamma: Tensor, beta: Tensor,
-                   eps: float, silu: bool, partial: Tensor, y: Tensor, groups: int = 32) -> Tensor:
-    assert x0.dtype == torch.bfloat16 and y.dtype == torch.bfloat16 and partial.dtype == torch.float32
-    assert partial.numel() >= gn_partial_floats(nb, hw, groups)
+                   eps: float, silu: bool, y: Tensor, groups: int = 32) -> Tensor:
+    assert x0.dtype == torch.bfloat16 and y.dtype == torch.bfloat16
     assert gamma.numel() == c0 + c1 and gamma.dtype == torch.float32
     info = {"desc": f"nb{nb} hw{hw} c{c0}+{c1}", "bytes": 4.0 * nb * hw * (c0 + c1)} if _lib.PROFILE is not None else None
     call("b200_groupnorm_silu", ptr(x0), c0, ptr(x1) if c1 else None, c1, nb, hw, groups, ptr(gamma), ptr(beta),
-         float(eps), int(silu), ptr(partial), ptr(y), stream(), info=info)
+         float(eps), int(silu), ptr(y), stream(), info=info)
     return y
 
 

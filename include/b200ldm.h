@@ -45,12 +45,11 @@ int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, const void* a
                    int out_fp32, int geglu, int block_n, int max_ctas, void* stream);
 
 /* GroupNorm (+ optional SiLU) over one or two NHWC sources (cat along C is never materialised).
- * partial: scratch of nb * b200_gn_nslab(hw) * groups * 2 floats.
+ * One launch: a thread-block cluster per image exchanges the group statistics through DSMEM.
  * Replaces F.group_norm + F.silu in ResnetBlock2D / Transformer2DModel.norm / conv_norm_out
  * (diffusers, via train_audioldm_lora.py:539-546). */
-int b200_gn_nslab(int hw);
 int b200_groupnorm_silu(const void* x0, int c0, const void* x1, int c1, int nb, int hw, int groups,
-                        const float* gamma, const float* beta, float eps, int silu, float* partial, void* y,
+                        const float* gamma, const float* beta, float eps, int silu, void* y,
                         void* stream);
 
 /* LayerNorm over the last dim of a [m, c] bf16 matrix.  Replaces F.layer_norm in
@@ -69,12 +68,13 @@ int b200_attention(const void* qkv, void* out, int batch, int seq, int heads, in
 /* Timestep / class embedding (K12): emb = cat([time_embedding(sinusoid(t)), class_embedding(labels)]).
  * t_steps: device float table; step_ptr: device int (nullable => index 0); t index = *step_ptr when
  * per_sample == 0, else t_steps[b].  Writes emb fp32 [nb, 2*ted] (nullable) and silu(emb) bf16
- * [nb, 2*ted].  Weights fp32 row-major [out, in].
+ * [nb, 2*ted].  Weights fp32, TRANSPOSED to row-major [in, out] (w1t [tproj, ted], w2t [ted, ted],
+ * wct [class_in, ted]) so the kernel's loads coalesce.
  * Replaces Timesteps + TimestepEmbedding + class_embedding in UNet2DConditionModel.forward
  * (class_labels=prompt_embeds: train_audioldm_lora.py:543). */
 int b200_time_class_embed(const float* t_steps, const int* step_ptr, int per_sample, const float* labels, int nb,
-                          int tproj, int ted, int class_in, const float* w1, const float* b1, const float* w2,
-                          const float* b2, const float* wc, const float* bc, float* emb, void* silu_emb,
+                          int tproj, int ted, int class_in, const float* w1t, const float* b1, const float* w2t,
+                          const float* b2, const float* wct, const float* bc, float* emb, void* silu_emb,
                           void* stream);
 
 /* Layout helpers.  nchw fp32 [nb, c, hw] -> nhwc bf16 [nb, hw, c_pad] (only the first c channels are

@@ -54,11 +54,7 @@ def conv_gemm(pw, a0, nb, h, w, out, *, a1=None, a2=None, stride=1, rowvec=None,
     return out
 
 
-def gn_partial_floats(nb, hw, groups=32):
-    return nb * 32 * groups * 2
-
-
-def groupnorm_silu(x0, c0, x1, c1, nb, hw, gamma, beta, eps, silu, partial, y, groups=32):
+def groupnorm_silu(x0, c0, x1, c1, nb, hw, gamma, beta, eps, silu, y, groups=32):
     x = x0.view(nb, hw, c0).float()
     if c1:
         x = torch.cat([x, x1.view(nb, hw, c1).float()], -1)
@@ -89,8 +85,8 @@ def time_class_embed(t_steps, step_ptr, per_sample, labels, nb, tproj, ted, clas
     freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
     arg = t[:, None].float() * freqs[None]
     e = torch.cat([torch.cos(arg), torch.sin(arg)], -1)
-    e = F.linear(F.silu(F.linear(e, w1, b1)), w2, b2)
-    c = F.linear(labels, wc, bc)
+    e = F.linear(F.silu(F.linear(e, w1.t(), b1)), w2.t(), b2)       # weights arrive transposed ([in, out])
+    c = F.linear(labels, wc.t(), bc)
     full = torch.cat([e, c], -1)
     if emb is not None:
         emb.copy_(full)
@@ -167,7 +163,7 @@ def mse_partial(pred, target, out_sum):
 
 def install(monkeypatch, ops_module):
     """Replace the kernel wrappers of `ops_module` (keeps PackedWeight / tiling helpers)."""
-    for name in ("conv_gemm", "gn_partial_floats", "groupnorm_silu", "layernorm", "attention", "time_class_embed",
+    for name in ("conv_gemm", "groupnorm_silu", "layernorm", "attention", "time_class_embed",
                  "pack_nchw_to_nhwc", "unpack_nhwc_to_nchw", "upsample_nearest", "sampler_step", "add_noise",
                  "adamw_flat", "mse_partial"):
         monkeypatch.setattr(ops_module, name, globals()[name])

@@ -63,7 +63,7 @@ def test_choose_block_n_valid():
         for mt in (1, 8, 32, 125, 512):
             for geglu in (False, True):
                 bn = ops.choose_block_n(n, mt, geglu)
-                assert 32 <= bn <= 256 and bn % (64 if geglu else 32) == 0
+                assert 64 <= bn <= 256 and bn % (128 if geglu else 64) == 0
 
 
 def test_conv_weight_k_order_and_geglu_interleave():
