@@ -22,7 +22,7 @@ namespace b200 {
 
 static constexpr int kGnThreads = 512;
 static constexpr int kMaxC = 2560;          // cat(1280, 1280) at AudioLDM-L
-static constexpr int kGnUnroll = 4;
+static constexpr int kGnUnroll = 8;
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);

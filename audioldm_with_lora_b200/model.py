@@ -87,6 +87,10 @@ class Attention(nn.Module):
 
     def set_processor(self, processor) -> None:
         self.processor = processor
+        # a foreign (torch) processor reads this module's weights: keep them where the activations are
+        dev = getattr(self, "b200_device", None)
+        if dev is not None and dev.type == "cuda" and not isinstance(processor, B200AttnProcessor):
+            self.to(dev)
 
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kw):
         return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states,
@@ -213,6 +217,7 @@ class UNet2DConditionModel(nn.Module):
             a.to_out[0].weight.data.copy_(self._sd[p + ".to_out.0.weight"])
             a.to_out[0].bias.data.copy_(self._sd[p + ".to_out.0.bias"])
             a.requires_grad_(False)
+            a.b200_device = self.b200_device
             self._attn[p] = a
             mods[p.replace(".", "__")] = a
         self.attn_modules = mods
@@ -263,6 +268,8 @@ class UNet2DConditionModel(nn.Module):
                 else:
                     setattr(holder, attr, cur)
             cur.update_layer(adapter_name, e.A, e.B, e.alpha)
+            if cur.base_layer.weight.is_cuda:
+                cur.to(cur.base_layer.weight.device)
             self._adapters[path] = e
         self.engine.set_lora(self._adapters, self.engine.lora_scale)
 
