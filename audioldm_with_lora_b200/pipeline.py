@@ -229,7 +229,8 @@ class AudioLDMPipeline:
     # ------------------------------------------------------------------ tail
     def decode_latents(self, latents: Tensor) -> Tensor:
         z = (latents / self.vae.config.scaling_factor).to(self.tail_dtype)
-        return self.vae.decode(z)
+        out = self.vae.decode(z)
+        return out.sample if hasattr(out, "sample") else out       # diffusers' AutoencoderKL returns DecoderOutput
 
     def mel_spectrogram_to_waveform(self, mel: Tensor) -> Tensor:
         if mel.dim() == 4:
