@@ -39,6 +39,68 @@ struct AttnParams {
   int variant;              // bit0: swap LBO/SBO of K-major descs, bit1: swap for the MN-major V desc
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// max over one 128-column S row in TMEM (two 32-column loads in flight at a time)
+template <bool kMasked>
+__device__ __forceinline__ float row_max(uint32_t t_row, int kvalid) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 4; c += 2) {
+    uint32_t r0[32], r1[32];
+    tmem_ld_x32(t_row + c * 32, r0);
+    tmem_ld_x32(t_row + (c + 1) * 32, r1);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float a0 = __uint_as_float(r0[i]), a1 = __uint_as_float(r0[i + 1]);
+      float b0 = __uint_as_float(r1[i]), b1 = __uint_as_float(r1[i + 1]);
+      if (kMasked) {
+        if (c * 32 + i >= kvalid) a0 = -INFINITY;
+        if (c * 32 + i + 1 >= kvalid) a1 = -INFINITY;
+        if ((c + 1) * 32 + i >= kvalid) b0 = -INFINITY;
+        if ((c + 1) * 32 + i + 1 >= kvalid) b1 = -INFINITY;
+      }
+      m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1); m2 = fmaxf(m2, b0); m3 = fmaxf(m3, b1);
+    }
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// p = exp2(s * scale - m * scale) as bf16 into the K-major core-matrix smem tile; returns the fp32 row sum.
+// The next 32-column TMEM load is issued before the current one is processed.
+template <bool kMasked>
+__device__ __forceinline__ float exp_store(uint32_t t_row, uint8_t* sp_row, float scale_log2, float neg_m, int kvalid) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  uint32_t r[2][32];
+  tmem_ld_x32(t_row, r[0]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    tmem_wait_ld();
+    if (c + 1 < 4) tmem_ld_x32(t_row + (c + 1) * 32, r[(c + 1) & 1]);
+    const uint32_t(&cur)[32] = r[c & 1];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float e[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        e[i] = ex2_approx(fmaf(__uint_as_float(cur[g * 8 + i]), scale_log2, neg_m));
+        if (kMasked && c * 32 + g * 8 + i >= kvalid) e[i] = 0.f;
+      }
+      s0 += e[0] + e[4]; s1 += e[1] + e[5]; s2 += e[2] + e[6]; s3 += e[3] + e[7];
+      uint4 pk;
+      pk.x = pack_bf16x2(e[0], e[1]); pk.y = pack_bf16x2(e[2], e[3]);
+      pk.z = pack_bf16x2(e[4], e[5]); pk.w = pack_bf16x2(e[6], e[7]);
+      *reinterpret_cast<uint4*>(sp_row + (c * 4 + g) * 2048) = pk;
+    }
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
 template <int D>
 __device__ __forceinline__ void fold_o(uint32_t t_o, float (&acc)[kMaxD], float alpha) {
 #pragma unroll
@@ -182,21 +244,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
       const int kvalid = min(kKV, p.seq - j * kKV);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_x32(t_s + lane_off + c * 32, r);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float v = (c * 32 + i < kvalid) ? __uint_as_float(r[i]) : -INFINITY;
-          mx = fmaxf(mx, v);
-        }
-      }
+      // pass 1: row max (keys past the end of the sequence only exist in the last block)
+      const float mx = (kvalid == kKV) ? row_max<false>(t_s + lane_off, kvalid) : row_max<true>(t_s + lane_off, kvalid);
       const float m_new = fmaxf(m_run, mx);
-      const float alpha = exp2f((m_run - m_new) * p.scale_log2);
+      const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);
       const float neg_m = -m_new * p.scale_log2;
       // fold the previous block's P V (also guarantees sP is free again)
       if (j > 0) {
@@ -205,31 +256,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
         fold_o<D>(t_o + lane_off, acc, alpha_prev);
       }
       // pass 2: p = exp2(s * c - m * c) -> bf16 -> smem (K-major core matrices), row sum
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_x32(t_s + lane_off + c * 32, r);
-        tmem_wait_ld();
-        float pv[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, neg_m));
-          pv[i] = (c * 32 + i < kvalid) ? e : 0.f;
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 pk;
-          pk.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]);
-          pk.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
-          pk.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]);
-          pk.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
-          // the row sum uses the bf16-rounded probabilities the PV MMA will see
-          sum += bf16_lo(pk.x) + bf16_hi(pk.x) + bf16_lo(pk.y) + bf16_hi(pk.y) + bf16_lo(pk.z) + bf16_hi(pk.z) +
-                 bf16_lo(pk.w) + bf16_hi(pk.w);
-          *reinterpret_cast<uint4*>(sP + (c * 4 + g) * 2048 + row * 16) = pk;
-        }
-      }
+      const float sum = (kvalid == kKV) ? exp_store<false>(t_s + lane_off, sP + row * 16, p.scale_log2, neg_m, kvalid)
+                                        : exp_store<true>(t_s + lane_off, sP + row * 16, p.scale_log2, neg_m, kvalid);
       l_run = l_run * alpha + sum;
       m_run = m_new;
       alpha_prev = alpha;

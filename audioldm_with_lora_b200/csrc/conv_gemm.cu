@@ -57,6 +57,9 @@ struct ConvGemmParams {
   int stride;                       // 1, or 2: keep even (h, w) only (Downsample2D: k3 s2 p1)
   int Hout, Wout;
   int tma_out;                      // 1: bf16 stride-1 output through smem staging + TMA store
+  int ksplit;                       // > 1: split-K; work item = (split, m_tile, n_tile), fp32 partials to `out`
+  int kb_per_split;
+  size_t split_stride;              // elements between the partial-sum planes
 };
 
 // exact-erf GELU to ~2e-7 absolute (Abramowitz-Stegun 7.1.26 erfc; bf16 output rounding is 4e-3 relative):
@@ -96,7 +99,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.ksplit;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA0);
@@ -131,10 +134,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int n_tile = t % p.num_n_tiles;
-        const int m_tile = t / p.num_n_tiles;
+        const int m_tile = (t / p.num_n_tiles) % p.num_m_tiles;
+        const int split = t / (p.num_n_tiles * p.num_m_tiles);
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
         const int h0 = (m_tile % p.tiles_h) * p.BH;
         const int n0 = (m_tile / p.tiles_h) * p.BNI;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* a_dst = smem + s * stage_bytes;
           uint8_t* b_dst = a_dst + kABytes;
@@ -174,7 +180,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * p.block_n;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int split = t / (p.num_n_tiles * p.num_m_tiles);
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
@@ -185,7 +194,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
-            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
           }
           umma_commit(&empty_bar[s]);
           if (++s == p.stages) {
@@ -217,7 +226,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int buf = it & 1;
       const uint32_t use = it >> 1;
       const int n_tile = t % p.num_n_tiles;
-      const int m_tile = t / p.num_n_tiles;
+      const int m_tile = (t / p.num_n_tiles) % p.num_m_tiles;
+      const int split = t / (p.num_n_tiles * p.num_m_tiles);
       const int h_t = (m_tile % p.tiles_h) * p.BH;
       const int n_t = (m_tile / p.tiles_h) * p.BNI;
       const int h = h_t + hl;
@@ -330,7 +340,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                   v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
                 }
                 if (p.out_fp32) {
-                  float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ld + cg;
+                  float* o = reinterpret_cast<float*>(p.out) + split * p.split_stride + pix * p.out_ld + cg;
                   *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
                   *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
                 } else {
@@ -359,6 +369,37 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 }
 
+// Split-K second stage: out[pix, n] = sum_s ws[s][pix][n] (fixed order) + bias + rowvec[image] + residual -> bf16.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, size_t split_stride, int M, int n_valid, int ld_ws,
+                     const float* __restrict__ bias, const float* __restrict__ rowvec, int rowvec_ld, int hw,
+                     const __nv_bfloat16* __restrict__ residual, int res_ld, __nv_bfloat16* __restrict__ out, int out_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int vec_per_row = n_valid >> 3;
+  const size_t total = static_cast<size_t>(M) * vec_per_row;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = i / vec_per_row;
+    const int cg = static_cast<int>(i % vec_per_row) * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    for (int s = 0; s < ksplit; ++s) add8(v, ws + s * split_stride + pix * ld_ws + cg);
+    if (bias) add8(v, bias + cg);
+    if (rowvec) add8(v, rowvec + (pix / hw) * rowvec_ld + cg);
+    if (residual) {
+      const uint4 rr = *reinterpret_cast<const uint4*>(residual + pix * res_ld + cg);
+      v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+      v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+    }
+    uint4 pk;
+    pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+    pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + pix * out_ld + cg) = pk;
+  }
+}
+
 static int pick_box(int H, int W, int NB, int* BH, int* BNI) {
   if (W < 1 || W > 128 || (128 % W) != 0) return -1;
   long best = -1;
@@ -384,7 +425,7 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
                               int w, int ntaps, int stride, const void* wpacked, int n_pad, int n_valid,
                               const float* bias, const float* rowvec, int rowvec_ld, const void* residual, int res_ld,
                               void* out, int out_ld, int out_fp32, int geglu, int block_n, int max_ctas,
-                              void* stream_v) {
+                              int ksplit, float* workspace, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(stride == 1 || (stride == 2 && ntaps == 9 && !residual), "conv_gemm: stride %d unsupported", stride);
   B200_CHECK_ARG(a0 && wpacked && out, "conv_gemm: null pointer");
@@ -397,6 +438,9 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
   B200_CHECK_ARG(!geglu || (block_n % 128 == 0 && !out_fp32 && !residual && !rowvec && stride == 1), "conv_gemm: geglu constraints");
   B200_CHECK_ARG(nb > 0 && h > 0 && w > 0, "conv_gemm: empty activation");
   B200_CHECK_ARG(out_ld % 8 == 0, "conv_gemm: out_ld %d must be a multiple of 8", out_ld);
+  if (ksplit < 1) ksplit = 1;
+  B200_CHECK_ARG(ksplit == 1 || (workspace && stride == 1 && !geglu && !out_fp32),
+                 "conv_gemm: split-K needs a workspace, stride 1, bf16 output, no GEGLU");
 
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
@@ -419,6 +463,17 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.res_ld = res_ld;
   p.out = out; p.out_ld = out_ld; p.out_fp32 = out_fp32; p.geglu = geglu;
   p.tma_out = (!out_fp32 && stride == 1 && block_n % 64 == 0) ? 1 : 0;
+  p.ksplit = 1;
+  p.kb_per_split = p.num_kb;
+  const size_t m_total = static_cast<size_t>(nb) * h * w;
+  if (ksplit > 1) {
+    p.kb_per_split = (p.num_kb + ksplit - 1) / ksplit;
+    p.ksplit = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;      // no empty splits
+    p.split_stride = m_total * n_pad;
+    // stage 1 writes raw fp32 partial sums [split][pixel][n_pad]; the epilogue terms move to the reduce kernel
+    p.bias = nullptr; p.rowvec = nullptr; p.residual = nullptr;
+    p.out = workspace; p.out_ld = n_pad; p.out_fp32 = 1; p.tma_out = 0;
+  }
   int tc = 32;
   while (tc < 2 * block_n) tc *= 2;
   p.tmem_cols = tc;
@@ -470,10 +525,20 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   }
-  int grid = p.num_m_tiles * p.num_n_tiles;
+  int grid = p.num_m_tiles * p.num_n_tiles * p.ksplit;
   int cap = max_ctas > 0 ? max_ctas : num_sms;
   if (grid > cap) grid = cap;
   B200_CHECK_PDL("conv_gemm", launch_pdl(conv_gemm_kernel, dim3(grid), dim3(kThreads), (size_t)smem_bytes, stream, 0,
                                          tA[0], tA[1], tA[2], tB, tO, p));
+  if (p.ksplit > 1) {
+    const size_t total = m_total * (n_valid / 8);
+    int rgrid = static_cast<int>((total + 255) / 256);
+    if (rgrid > num_sms * 8) rgrid = num_sms * 8;
+    B200_CHECK_PDL("conv_gemm(split-K reduce)",
+                   launch_pdl(splitk_reduce_kernel, dim3(rgrid), dim3(256), 0, stream, 0, workspace, p.ksplit,
+                              p.split_stride, (int)m_total, n_valid, n_pad, bias, rowvec, rowvec_ld, h * w,
+                              reinterpret_cast<const __nv_bfloat16*>(residual), res_ld,
+                              reinterpret_cast<__nv_bfloat16*>(out), out_ld));
+  }
   return B200_OK;
 }

@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace b200 {
@@ -92,9 +93,12 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[na].val.programmaticStreamSerializationAllowed = 1;
-  ++na;
+  static const bool no_pdl = getenv("B200_NO_PDL") != nullptr;      // debugging knob
+  if (!no_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   if (cluster_x > 0) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = cluster_x;

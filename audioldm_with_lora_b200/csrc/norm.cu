@@ -40,7 +40,8 @@ struct GnParams {
   __nv_bfloat16* y;
 };
 
-// grid (cluster_size, NB), cluster (cluster_size, 1, 1): blockIdx.x = rank of the CTA in its image's cluster.
+// grid (cluster_size, NB, gsplit), cluster (cluster_size, 1, 1): blockIdx.x = rank of the CTA in its cluster
+// (pixel slab), blockIdx.z = which 1/gsplit of the groups (= a contiguous channel range) the cluster owns.
 __global__ void __launch_bounds__(kGnThreads)
 groupnorm_silu_kernel(const GnParams p) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -50,19 +51,23 @@ groupnorm_silu_kernel(const GnParams p) {
   const int rank = blockIdx.x;
   const int n = blockIdx.y;
   const int C = p.C0 + p.C1;
-  const int vpp = C >> 3;                           // 16-byte vectors per pixel
+  const int Cs = C / gridDim.z;                     // channels owned by this cluster
+  const int c_base = blockIdx.z * Cs;
+  const int gl = p.groups / gridDim.z;              // groups owned by this cluster
+  const int vpp = Cs >> 3;                          // 16-byte vectors per pixel (this cluster's share)
   const int nlanes = kGnThreads / vpp;              // pixel lanes per CTA (>= 1: C <= 2560)
   const int tid = threadIdx.x;
   const bool active = tid < nlanes * vpp;
   const int v = tid % vpp;
   const int lane = tid / vpp;
-  const int c = v * 8;
+  const int lc = v * 8;                             // channel inside the cluster's range
+  const int c = c_base + lc;                        // channel of the (concatenated) tensor
   const int cpg = C / p.groups;
 
-  __shared__ float s_sum[kGnThreads * 8];           // [lane][C]
+  __shared__ float s_sum[kGnThreads * 8];           // [lane][Cs]
   __shared__ float s_sq[kGnThreads * 8];
   __shared__ float s_gpart[128];                    // this CTA's per-group {sum, sumsq}; read by cluster peers
-  __shared__ float s_mean[64], s_rstd[64];
+  __shared__ float s_mean[32], s_rstd[32];
 
   const int pps = (p.HW + nrank - 1) / nrank;
   const int p_begin = rank * pps;
@@ -95,8 +100,8 @@ groupnorm_silu_kernel(const GnParams p) {
         }
       }
     }
-    float* ds = s_sum + lane * C + c;
-    float* dq = s_sq + lane * C + c;
+    float* ds = s_sum + lane * Cs + lc;
+    float* dq = s_sq + lane * Cs + lc;
     *reinterpret_cast<float4*>(ds) = make_float4(a[0], a[1], a[2], a[3]);
     *reinterpret_cast<float4*>(ds + 4) = make_float4(a[4], a[5], a[6], a[7]);
     *reinterpret_cast<float4*>(dq) = make_float4(b[0], b[1], b[2], b[3]);
@@ -104,17 +109,17 @@ groupnorm_silu_kernel(const GnParams p) {
   }
   __syncthreads();
   // lanes -> per-channel totals (fixed order), kept in lane 0's row
-  for (int ch = tid; ch < C; ch += kGnThreads) {
+  for (int ch = tid; ch < Cs; ch += kGnThreads) {
     float s = 0.f, q = 0.f;
     for (int l = 0; l < nlanes; ++l) {
-      s += s_sum[l * C + ch];
-      q += s_sq[l * C + ch];
+      s += s_sum[l * Cs + ch];
+      q += s_sq[l * Cs + ch];
     }
     s_sum[ch] = s;
     s_sq[ch] = q;
   }
   __syncthreads();
-  if (tid < 2 * p.groups) {
+  if (tid < 2 * gl) {
     const int g = tid >> 1;
     const float* srcv = (tid & 1) ? s_sq : s_sum;
     float s = 0.f;
@@ -123,14 +128,14 @@ groupnorm_silu_kernel(const GnParams p) {
   }
   cluster.sync();
   // ---- cluster exchange through DSMEM (fixed rank order)
-  if (tid < 2 * p.groups) {
+  if (tid < 2 * gl) {
     float s = 0.f;
     for (int r = 0; r < nrank; ++r) s += cluster.map_shared_rank(s_gpart, r)[tid];
     s_gpart[64 + tid] = s;                          // local copy of the totals (peers read [0, 64) only)
   }
   __syncthreads();
   cluster.barrier_arrive();                         // peers may exit once everyone has read their partials
-  if (tid < p.groups) {
+  if (tid < gl) {
     const float cnt = static_cast<float>(p.HW) * cpg;
     const float mean = s_gpart[64 + 2 * tid] / cnt;
     const float var = fmaxf(s_gpart[64 + 2 * tid + 1] / cnt - mean * mean, 0.f);
@@ -144,7 +149,7 @@ groupnorm_silu_kernel(const GnParams p) {
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (c + j) / cpg;
+      const int g = (lc + j) / cpg;
       sc[j] = p.gamma[c + j] * s_rstd[g];
       sh[j] = p.beta[c + j] - s_mean[g] * sc[j];
     }
@@ -261,9 +266,43 @@ extern "C" int b200_groupnorm_silu(const void* x0, int c0, const void* x1, int c
   p.x0 = reinterpret_cast<const __nv_bfloat16*>(x0); p.x1 = reinterpret_cast<const __nv_bfloat16*>(x1);
   p.C0 = c0; p.C1 = c1; p.HW = hw; p.groups = groups; p.gamma = gamma; p.beta = beta; p.eps = eps; p.silu = silu;
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
-  int cs = 8;
-  while (cs > 1 && hw < 4 * cs) cs >>= 1;           // at least 4 pixels per CTA of the cluster
-  B200_CHECK_PDL("groupnorm", launch_pdl(groupnorm_silu_kernel, dim3(cs, nb, 1), dim3(kGnThreads), 0, stream, cs, p));
+  // Launch shape: cluster size cs (pixel slabs of one image) x gsplit (independent halves / quarters of the
+  // groups), the combination with the most CTAs whose clusters are all co-resident (one wave).
+  static int max_active[4] = {-1, -1, -1, -1};      // for cs = 1, 2, 4, 8
+  static const int max_cs = getenv("B200_GN_CLUSTER") ? atoi(getenv("B200_GN_CLUSTER")) : 8;   // debugging knob
+  int best_cs = 1, best_gs = 1, best_ctas = 0;
+  for (int ci = 3; ci >= 0; --ci) {
+    const int cs = 1 << ci;
+    if (cs > max_cs || (cs > 1 && hw < 4 * cs)) continue;
+    if (max_active[ci] < 0) {
+      cudaLaunchConfig_t qc;
+      memset(&qc, 0, sizeof(qc));
+      qc.gridDim = dim3(cs, 1, 1);
+      qc.blockDim = dim3(kGnThreads, 1, 1);
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = cs; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa;
+      qc.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, groupnorm_silu_kernel, &qc) != cudaSuccess || nclusters <= 0) {
+        cudaGetLastError();
+        nclusters = 0;
+      }
+      max_active[ci] = nclusters;
+    }
+    for (int gs = 1; gs <= 4; gs *= 2) {
+      if (groups % gs != 0 || (C / gs) % 8 != 0) continue;
+      if (nb * gs > max_active[ci]) continue;
+      const int ctas = nb * gs * cs;
+      if (ctas > best_ctas) {                        // ties keep the larger cluster / smaller split seen first
+        best_ctas = ctas; best_cs = cs; best_gs = gs;
+      }
+    }
+  }
+  if (best_ctas == 0) { best_cs = 1; best_gs = 1; }  // more images than co-resident CTAs: plain multi-wave launch
+  B200_CHECK_PDL("groupnorm", launch_pdl(groupnorm_silu_kernel, dim3(best_cs, nb, best_gs), dim3(kGnThreads), 0, stream,
+                                         best_cs, p));
   return B200_OK;
 }
 

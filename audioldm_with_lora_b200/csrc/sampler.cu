@@ -137,6 +137,7 @@ time_class_embed_kernel(const float* __restrict__ t_steps, const int* __restrict
     for (int o = threadIdx.x; o < ted; o += kEmbThreads) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       int k = 0;
+#pragma unroll 8
       for (; k + 3 < tproj; k += 4) {
         a0 = fmaf(w1t[static_cast<size_t>(k) * ted + o], s_sin[k], a0);
         a1 = fmaf(w1t[static_cast<size_t>(k + 1) * ted + o], s_sin[k + 1], a1);
@@ -153,6 +154,7 @@ time_class_embed_kernel(const float* __restrict__ t_steps, const int* __restrict
     const int k0 = ks * kper, k1 = min(ted, k0 + kper);
     float a0 = 0.f, a1 = 0.f;
     int k = k0;
+#pragma unroll 16
     for (; k + 1 < k1; k += 2) {
       a0 = fmaf(w2t[static_cast<size_t>(k) * ted + o], s_h[k], a0);
       a1 = fmaf(w2t[static_cast<size_t>(k + 1) * ted + o], s_h[k + 1], a1);
@@ -167,6 +169,7 @@ time_class_embed_kernel(const float* __restrict__ t_steps, const int* __restrict
     const int k0 = ks * kper, k1 = min(class_in, k0 + kper);
     float a0 = 0.f, a1 = 0.f;
     int k = k0;
+#pragma unroll 16
     for (; k + 1 < k1; k += 2) {
       a0 = fmaf(wct[static_cast<size_t>(k) * ted + o], s_lab[k], a0);
       a1 = fmaf(wct[static_cast<size_t>(k + 1) * ted + o], s_lab[k + 1], a1);

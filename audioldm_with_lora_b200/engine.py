@@ -129,10 +129,14 @@ class UNetEngine:
             self._plans[key] = self._build_plan(nb, h, w)
         return self._plans[key]
 
-    def _pw(self, segs, bias, m_tiles, ntaps, c0, c1=0, c2=0, geglu=False, block_n=None) -> PackedWeight:
+    def _pw(self, segs, bias, m_tiles, ntaps, c0, c1=0, c2=0, geglu=False, block_n=None, split=True) -> PackedWeight:
         n = segs[0].shape[0]
-        bn = block_n or ops.choose_block_n(n, m_tiles, geglu)
-        return packing.pack(segs, bias, bn, ntaps, c0, c1, c2, geglu, device=self.device)
+        num_kb = (ntaps * c0 + c1 + c2) // 64
+        if block_n:
+            bn, ks = block_n, 1
+        else:
+            bn, ks = ops.choose_tiling(n, m_tiles, num_kb, geglu, allow_split=split)
+        return packing.pack(segs, bias, bn, ntaps, c0, c1, c2, geglu, device=self.device, ksplit=ks)
 
     def _build_plan(self, nb: int, h: int, w: int) -> dict:
         cfg, sd, g = self.cfg, self.sd, self.graph
@@ -290,6 +294,11 @@ class UNetEngine:
             return ops.groupnorm_silu(x0, c0, x1, c1, nb, hh * ww, S[name + ".weight"], S[name + ".bias"], eps, silu,
                                       y, cfg.groups)
 
+        def splitk_ws(pw, lvl, stride=1, fp32=False):
+            if pw.ksplit > 1 and stride == 1 and not fp32:
+                return ar.alloc((pw.ksplit * M(lvl) * pw.n_pad,), torch.float32)
+            return None
+
         def conv(name, a0, lvl, *, a1=None, a2=None, rowvec_off=None, residual=None, stride=1, out=None,
                  out_lvl=None):
             pw = W[name]
@@ -297,13 +306,19 @@ class UNetEngine:
             if out is None:
                 out = ar.alloc((M(out_lvl if out_lvl is not None else lvl), pw.n_valid), bf16)
             rv = rowvec[:, rowvec_off:] if rowvec_off is not None else None
-            return ops.conv_gemm(pw, a0, nb, hh, ww, out, a1=a1, a2=a2, stride=stride, rowvec=rv,
-                                 rowvec_ld=plan["temb_total"], residual=residual)
+            ws = splitk_ws(pw, lvl, stride, out.dtype == torch.float32)
+            ops.conv_gemm(pw, a0, nb, hh, ww, out, a1=a1, a2=a2, stride=stride, rowvec=rv,
+                          rowvec_ld=plan["temb_total"], residual=residual, workspace=ws)
+            ar.release(ws)
+            return out
 
         def linear(name, a0, lvl, *, a1=None, residual=None):
             pw = W[name]
             out = ar.alloc((M(lvl), pw.n_valid), bf16)
-            return ops.conv_gemm(pw, a0, 1, M(lvl), 1, out, a1=a1, residual=residual)
+            ws = splitk_ws(pw, lvl)
+            ops.conv_gemm(pw, a0, 1, M(lvl), 1, out, a1=a1, residual=residual, workspace=ws)
+            ar.release(ws)
+            return out
 
         def resnet(r: ResnetDesc, x0, x1, lvl):
             c_h = r.cin - r.skip_c

@@ -30,6 +30,7 @@ class PackedWeight:
     c1: int = 0
     c2: int = 0
     geglu: bool = False
+    ksplit: int = 1               # > 1: split-K over this many CTAs per tile (small-M, long-K layers)
     alg_macs_per_row: Optional[float] = None   # algorithmic (unpadded) N*K of the layer; default: stored N*K
 
     @property
@@ -80,9 +81,37 @@ def choose_block_n(n: int, m_tiles: int, geglu: bool = False) -> int:
     return best
 
 
+def _kb_cycles(bn: int) -> float:
+    """Cycles one 64-deep K block costs a CTA: tcgen05 time (2*bn) or operand fetch (bytes / ~55 B/clk, the
+    latency-bound TMA rate measured with 4-8 stages in flight), whichever is larger."""
+    return max(2.0 * bn, (16384 + bn * 128) / 55.0)
+
+
+def choose_tiling(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_split: bool = True) -> Tuple[int, int]:
+    """(block_n, ksplit) minimising a wave/cycle model on 148 SMs; split-K only when it wins by > 25 %."""
+    step = 128 if geglu else 64
+    best = {}
+    for ks in (1, 2, 3, 4):
+        if ks > 1 and (not allow_split or geglu or num_kb < 16 * ks // 2):
+            continue
+        for bn in range(step, 257, step):
+            tiles1 = m_tiles * math.ceil(n / bn)
+            if ks > 1 and tiles1 > NUM_SMS // 2:
+                continue
+            waves = math.ceil(tiles1 * ks / NUM_SMS)
+            cost = waves * (math.ceil(num_kb / ks) * _kb_cycles(bn) + 2 * bn) + 4000 + (7000 if ks > 1 else 0)
+            key = 1 if ks == 1 else 2
+            if key not in best or cost < best[key][0] - 1e-9:
+                best[key] = (cost, bn, ks)
+    if 2 in best and best[2][0] < 0.75 * best[1][0]:
+        return best[2][1], best[2][2]
+    return best[1][1], 1
+
+
 def conv_gemm(pw: PackedWeight, a0: Tensor, nb: int, h: int, w: int, out: Tensor, *, a1: Optional[Tensor] = None,
               a2: Optional[Tensor] = None, stride: int = 1, rowvec: Optional[Tensor] = None, rowvec_ld: int = 0,
-              residual: Optional[Tensor] = None, out_ld: Optional[int] = None, max_ctas: int = 0) -> Tensor:
+              residual: Optional[Tensor] = None, out_ld: Optional[int] = None, max_ctas: int = 0,
+              workspace: Optional[Tensor] = None) -> Tensor:
     """out[pix, :n_valid] = epilogue(implicit GEMM); see include/b200ldm.h::b200_conv_gemm."""
     assert a0.dtype == torch.bfloat16 and a0.is_contiguous()
     assert a0.numel() == nb * h * w * pw.c0, (a0.shape, nb, h, w, pw.c0)
@@ -97,14 +126,18 @@ def conv_gemm(pw: PackedWeight, a0: Tensor, nb: int, h: int, w: int, out: Tensor
     if residual is not None:
         assert residual.dtype == torch.bfloat16
         res_ld = pw.n_valid
+    ksplit = pw.ksplit if workspace is not None else 1
+    if ksplit > 1:
+        assert workspace.dtype == torch.float32 and workspace.numel() >= ksplit * nb * h * w * pw.n_pad
     info = None
     if _lib.PROFILE is not None:
         m_out = nb * h * w if stride == 1 else nb * ((h - 1) // 2 + 1) * ((w - 1) // 2 + 1)
         info = {"flops": 2.0 * m_out * pw.macs_per_row, "m": nb * h * w, "n": pw.n_valid,
-                "k": pw.k, "bn": pw.block_n, "taps": pw.ntaps}
+                "k": pw.k, "bn": pw.block_n, "taps": pw.ntaps, "desc": f"ks{ksplit}" if ksplit > 1 else None}
     call("b200_conv_gemm", ptr(a0), pw.c0, ptr(a1) if pw.c1 else None, pw.c1, ptr(a2) if pw.c2 else None, pw.c2,
          nb, h, w, pw.ntaps, stride, ptr(pw.w), pw.n_pad, pw.n_valid, ptr(pw.bias), ptr(rowvec), rowvec_ld,
-         ptr(residual), res_ld, ptr(out), ld, int(out_fp32), int(pw.geglu), pw.block_n, max_ctas, stream(), info=info)
+         ptr(residual), res_ld, ptr(out), ld, int(out_fp32), int(pw.geglu), pw.block_n, max_ctas, ksplit,
+         ptr(workspace) if ksplit > 1 else None, stream(), info=info)
     return out
 
 

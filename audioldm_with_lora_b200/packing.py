@@ -37,7 +37,7 @@ def pad_k(w: Tensor, k_pad: int) -> Tensor:
 
 
 def pack(segments: Sequence[Tensor], bias: Optional[Tensor], block_n: int, ntaps: int, c0: int, c1: int = 0,
-         c2: int = 0, geglu: bool = False, device=None) -> PackedWeight:
+         c2: int = 0, geglu: bool = False, device=None, ksplit: int = 1) -> PackedWeight:
     """segments: fp32 [N, K_i] matrices concatenated along K (already tap-major / channel-padded)."""
     w = torch.cat([s.float() for s in segments], dim=1)
     n, k = w.shape
@@ -68,7 +68,7 @@ def pack(segments: Sequence[Tensor], bias: Optional[Tensor], block_n: int, ntaps
     dev = device if device is not None else w.device
     return PackedWeight(w=w.to(dev, torch.bfloat16).contiguous(),
                         bias=None if b is None else b.to(dev, torch.float32).contiguous(),
-                        n_valid=n_valid, block_n=block_n, ntaps=ntaps, c0=c0, c1=c1, c2=c2, geglu=geglu)
+                        n_valid=n_valid, block_n=block_n, ntaps=ntaps, c0=c0, c1=c1, c2=c2, geglu=geglu, ksplit=ksplit)
 
 
 def lora_pad(r_total: int) -> int:

@@ -17,7 +17,7 @@ def main():
     rows = [(x["Kernel Name"], float(x["Metric Value"]), x["Grid Size"]) for x in csv.DictReader(lines)]
     idx = [i for i, (n, _, _) in enumerate(rows) if "sampler_step" in n]
     # the last pair of consecutive sampler launches with only this library's kernels in between
-    mine = ("conv_gemm", "attention_kernel", "groupnorm", "layernorm", "time_class_embed", "upsample_nearest", "sampler_step")
+    mine = ("conv_gemm", "attention_kernel", "groupnorm", "gn_", "layernorm", "time_class_embed", "upsample_nearest", "sampler_step")
     step = None
     for a, b in reversed(list(zip(idx[:-1], idx[1:]))):
         cand = rows[a + 1: b + 1]
