@@ -30,7 +30,7 @@ _PROTOS = {
     "b200_last_error": (c_char_p, []),
     "b200_conv_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
-                               c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+                               c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "b200_groupnorm_silu": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
                                     c_int, c_void_p, c_void_p]),
     "b200_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),

@@ -17,6 +17,11 @@
 //   + residual, optional GEGLU (K3).  bf16 results are staged in a per-warp 128B-swizzled smem
 //   tile and written with TMA stores (coalesced, asynchronous, tails clipped by the tensor map);
 //   fp32 / stride-2 outputs use direct 16-byte stores.
+// * 2-CTA mode (cta_group::2, clusters of two CTAs on neighbouring SMs): the pair computes one
+//   256 x block_n tile; each CTA stages its own 128 rows of A and HALF of the weight tile, the leader
+//   issues tcgen05.mma.cta_group::2 reading both CTAs' shared memory.  Halves the weight traffic per
+//   CTA and the smem per stage (6 stages instead of 4 at block_n = 256): the kernel is bound by
+//   operand bytes in flight, not by the tensor pipe.
 // * Programmatic dependent launch: the prologue (barrier init, TMEM alloc, descriptor prefetch)
 //   overlaps the tail of the previous kernel in the stream / CUDA graph.
 //
@@ -57,6 +62,7 @@ struct ConvGemmParams {
   int stride;                       // 1, or 2: keep even (h, w) only (Downsample2D: k3 s2 p1)
   int Hout, Wout;
   int tma_out;                      // 1: bf16 stride-1 output through smem staging + TMA store
+  int num_m_groups;                 // m-tiles (1-CTA) or pairs of m-tiles (2-CTA) the tile index runs over
   int ksplit;                       // > 1: split-K; work item = (split, m_tile, n_tile), fp32 partials to `out`
   int kb_per_split;
   size_t split_stride;              // elements between the partial-sum planes
@@ -82,6 +88,7 @@ __device__ __forceinline__ void add8(float (&v)[8], const float* src) {
   v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
 }
 
+template <bool kCta2>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
@@ -89,7 +96,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024B alignment for the 128B swizzle atoms.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = kABytes + p.block_n * kBlockK * 2;
+  const uint32_t cta_rank = kCta2 ? cluster_ctarank() : 0u;       // 0 = leader of the pair
+  const int b_rows = kCta2 ? p.block_n / 2 : p.block_n;           // weight rows this CTA stages per k-block
+  const int stage_bytes = kABytes + b_rows * kBlockK * 2;
   uint8_t* epi_smem = smem + p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * kEpiStageBytes);
   uint64_t* empty_bar = full_bar + p.stages;
@@ -99,7 +108,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.ksplit;
+  const int num_tiles = p.num_m_groups * p.num_n_tiles * p.ksplit;  // work items of a CTA (1-CTA) / a pair (2-CTA)
+  const int tile0 = kCta2 ? blockIdx.x >> 1 : blockIdx.x;
+  const int tile_step = kCta2 ? gridDim.x >> 1 : gridDim.x;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA0);
@@ -111,16 +122,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], kEpiWarps * 32);
+      mbar_init(&tempty_bar[b], kCta2 ? 2 * kEpiWarps : kEpiWarps);   // one arrival per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, p.tmem_cols);
-    tmem_relinquish();
+    if (kCta2) {
+      tmem_alloc2(tmem_slot, p.tmem_cols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, p.tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCta2) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // PDL: everything above overlapped the previous kernel's tail; from here on we touch its outputs.
@@ -132,34 +149,48 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = tile0; t < num_tiles; t += tile_step) {
         const int n_tile = t % p.num_n_tiles;
-        const int m_tile = (t / p.num_n_tiles) % p.num_m_tiles;
-        const int split = t / (p.num_n_tiles * p.num_m_tiles);
+        const int m_group = (t / p.num_n_tiles) % p.num_m_groups;
+        const int m_tile = kCta2 ? 2 * m_group + static_cast<int>(cta_rank) : m_group;   // may be a phantom tile: all OOB
+        const int split = t / (p.num_n_tiles * p.num_m_groups);
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
         const int h0 = (m_tile % p.tiles_h) * p.BH;
         const int n0 = (m_tile / p.tiles_h) * p.BNI;
+        const int b_row0 = n_tile * p.block_n + static_cast<int>(cta_rank) * b_rows;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* a_dst = smem + s * stage_bytes;
           uint8_t* b_dst = a_dst + kABytes;
-          mbar_expect_tx(&full_bar[s], stage_bytes);
+          // 2-CTA: both CTAs' loads are credited to the leader's barrier, which expects the pair's bytes
+          if (!kCta2) mbar_expect_tx(&full_bar[s], stage_bytes);
+          else if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * stage_bytes);
+          int c0, c1 = 0, c2 = h0;
+          const CUtensorMap* tm;
           if (kb < p.seg_end0) {
             const int tap = kb / p.cb0;
             const int cb = kb - tap * p.cb0;
-            int dh = 0, dw = 0;
             if (p.ntaps == 9) {
-              dh = tap / 3 - 1;
-              dw = tap % 3 - 1;
+              c2 = h0 + tap / 3 - 1;
+              c1 = tap % 3 - 1;
             }
-            tma_load_4d(a_dst, &tmA0, &full_bar[s], cb * kBlockK, dw, h0 + dh, n0);
+            c0 = cb * kBlockK;
+            tm = &tmA0;
           } else if (kb < p.seg_end1) {
-            tma_load_4d(a_dst, &tmA1, &full_bar[s], (kb - p.seg_end0) * kBlockK, 0, h0, n0);
+            c0 = (kb - p.seg_end0) * kBlockK;
+            tm = &tmA1;
           } else {
-            tma_load_4d(a_dst, &tmA2, &full_bar[s], (kb - p.seg_end1) * kBlockK, 0, h0, n0);
+            c0 = (kb - p.seg_end1) * kBlockK;
+            tm = &tmA2;
           }
-          tma_load_2d(b_dst, &tmB, &full_bar[s], kb * kBlockK, n_tile * p.block_n);
+          if (kCta2) {
+            tma_load_4d_cta2(a_dst, tm, &full_bar[s], c0, c1, c2, n0);
+            tma_load_2d_cta2(b_dst, &tmB, &full_bar[s], kb * kBlockK, b_row0);
+          } else {
+            tma_load_4d(a_dst, tm, &full_bar[s], c0, c1, c2, n0);
+            tma_load_2d(b_dst, &tmB, &full_bar[s], kb * kBlockK, b_row0);
+          }
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
@@ -169,18 +200,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (one thread)
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0);
+    if (lane == 0 && cta_rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(kCta2 ? 2 * kBlockM : kBlockM, p.block_n, 0, 0);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int t = tile0; t < num_tiles; t += tile_step, ++it) {
         const int buf = it & 1;
         const uint32_t use = it >> 1;
         mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * p.block_n;
-        const int split = t / (p.num_n_tiles * p.num_m_tiles);
+        const int split = t / (p.num_n_tiles * p.num_m_groups);
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -194,15 +225,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
-            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
+            if (kCta2) umma_bf16_ss_cta2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
+            else umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
           }
-          umma_commit(&empty_bar[s]);
+          if (kCta2) umma_commit_cta2(&empty_bar[s], 3);     // frees the stage in both CTAs
+          else umma_commit(&empty_bar[s]);
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(&tfull_bar[buf]);
+        if (kCta2) umma_commit_cta2(&tfull_bar[buf], 3);     // both CTAs' epilogues own 128 rows each
+        else umma_commit(&tfull_bar[buf]);
       }
     }
   } else {
@@ -222,12 +256,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int half = p.block_n / 2;
     const int out_cols = p.geglu ? half : p.block_n;     // output columns per tile
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = tile0; t < num_tiles; t += tile_step, ++it) {
       const int buf = it & 1;
       const uint32_t use = it >> 1;
       const int n_tile = t % p.num_n_tiles;
-      const int m_tile = (t / p.num_n_tiles) % p.num_m_tiles;
-      const int split = t / (p.num_n_tiles * p.num_m_tiles);
+      const int m_group = (t / p.num_n_tiles) % p.num_m_groups;
+      const int m_tile = kCta2 ? 2 * m_group + static_cast<int>(cta_rank) : m_group;
+      const int split = t / (p.num_n_tiles * p.num_m_groups);
       const int h_t = (m_tile % p.tiles_h) * p.BH;
       const int n_t = (m_tile / p.tiles_h) * p.BNI;
       const int h = h_t + hl;
@@ -356,16 +391,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[buf]);
+      __syncwarp();
+      if (lane == 0) {
+        if (kCta2) mbar_arrive_cluster(leader_addr(&tempty_bar[buf]));   // the MMA issuer lives in the leader CTA
+        else mbar_arrive(&tempty_bar[buf]);
+      }
     }
     if (p.tma_out && lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kCta2) cluster_sync_all();      // nobody exits while the peer may still signal its barriers / read its smem
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (kCta2) tmem_dealloc2(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -425,7 +466,7 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
                               int w, int ntaps, int stride, const void* wpacked, int n_pad, int n_valid,
                               const float* bias, const float* rowvec, int rowvec_ld, const void* residual, int res_ld,
                               void* out, int out_ld, int out_fp32, int geglu, int block_n, int max_ctas,
-                              int ksplit, float* workspace, void* stream_v) {
+                              int ksplit, float* workspace, int cta_pair, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(stride == 1 || (stride == 2 && ntaps == 9 && !residual), "conv_gemm: stride %d unsupported", stride);
   B200_CHECK_ARG(a0 && wpacked && out, "conv_gemm: null pointer");
@@ -477,7 +518,11 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
   int tc = 32;
   while (tc < 2 * block_n) tc *= 2;
   p.tmem_cols = tc;
-  const int stage_bytes = kABytes + block_n * kBlockK * 2;
+  // 2-CTA pairs: needs two halves of >= 64 weight rows and more than one m-tile to pair up
+  const bool cta2 = cta_pair && block_n % 128 == 0 && p.num_m_tiles >= 2;
+  p.num_m_groups = cta2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
+  const int b_rows = cta2 ? block_n / 2 : block_n;
+  const int stage_bytes = kABytes + b_rows * kBlockK * 2;
   const int fixed = kEpiWarps * kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   p.stages = (kSmemLimit - fixed) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
@@ -498,7 +543,7 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
     const uint64_t K = static_cast<uint64_t>(p.num_kb) * 64;
     uint64_t dims[2] = {K, (uint64_t)n_pad};
     uint64_t strides[1] = {K};
-    uint32_t box[2] = {64, (uint32_t)block_n};
+    uint32_t box[2] = {64, (uint32_t)b_rows};
     int rc = make_tmap_bf16(&tB, wpacked, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -523,13 +568,21 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   }
-  int grid = p.num_m_tiles * p.num_n_tiles * p.ksplit;
+  int grid = p.num_m_groups * p.num_n_tiles * p.ksplit;
   int cap = max_ctas > 0 ? max_ctas : num_sms;
-  if (grid > cap) grid = cap;
-  B200_CHECK_PDL("conv_gemm", launch_pdl(conv_gemm_kernel, dim3(grid), dim3(kThreads), (size_t)smem_bytes, stream, 0,
-                                         tA[0], tA[1], tA[2], tB, tO, p));
+  if (cta2) {
+    if (grid > cap / 2) grid = cap / 2;
+    if (grid < 1) grid = 1;
+    B200_CHECK_PDL("conv_gemm(2-CTA)", launch_pdl(conv_gemm_kernel<true>, dim3(2 * grid), dim3(kThreads), (size_t)smem_bytes,
+                                                  stream, 2, tA[0], tA[1], tA[2], tB, tO, p));
+  } else {
+    if (grid > cap) grid = cap;
+    B200_CHECK_PDL("conv_gemm", launch_pdl(conv_gemm_kernel<false>, dim3(grid), dim3(kThreads), (size_t)smem_bytes, stream,
+                                           0, tA[0], tA[1], tA[2], tB, tO, p));
+  }
   if (p.ksplit > 1) {
     const size_t total = m_total * (n_valid / 8);
     int rgrid = static_cast<int>((total + 255) / 256);

@@ -6,6 +6,7 @@ stream; tensors are borrowed, outputs are caller-allocated.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -16,6 +17,7 @@ from ._lib import call, ptr, stream
 
 Tensor = torch.Tensor
 NUM_SMS = 148
+CTA_PAIR = os.environ.get("B200_CTA_PAIR", "1") != "0"     # 2-CTA (cta_group::2) GEMM tiles where the shape allows
 
 
 @dataclass
@@ -81,10 +83,11 @@ def choose_block_n(n: int, m_tiles: int, geglu: bool = False) -> int:
     return best
 
 
-def _kb_cycles(bn: int) -> float:
+def _kb_cycles(bn: int, pair: bool = False) -> float:
     """Cycles one 64-deep K block costs a CTA: tcgen05 time (2*bn) or operand fetch (bytes / ~55 B/clk, the
-    latency-bound TMA rate measured with 4-8 stages in flight), whichever is larger."""
-    return max(2.0 * bn, (16384 + bn * 128) / 55.0)
+    latency-bound TMA rate measured with 4-8 stages in flight), whichever is larger.  In 2-CTA mode a CTA
+    fetches its 128 A rows and only half of the weight tile."""
+    return max(2.0 * bn, (16384 + bn * (64 if pair else 128)) / 55.0)
 
 
 def choose_tiling(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_split: bool = True) -> Tuple[int, int]:
@@ -95,11 +98,12 @@ def choose_tiling(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_
         if ks > 1 and (not allow_split or geglu or num_kb < 16 * ks // 2):
             continue
         for bn in range(step, 257, step):
-            tiles1 = m_tiles * math.ceil(n / bn)
+            pair = CTA_PAIR and bn % 128 == 0 and m_tiles >= 2
+            tiles1 = (2 * math.ceil(m_tiles / 2) if pair else m_tiles) * math.ceil(n / bn)
             if ks > 1 and tiles1 > NUM_SMS // 2:
                 continue
             waves = math.ceil(tiles1 * ks / NUM_SMS)
-            cost = waves * (math.ceil(num_kb / ks) * _kb_cycles(bn) + 2 * bn) + 4000 + (7000 if ks > 1 else 0)
+            cost = waves * (math.ceil(num_kb / ks) * _kb_cycles(bn, pair) + 2 * bn) + 4000 + (7000 if ks > 1 else 0)
             key = 1 if ks == 1 else 2
             if key not in best or cost < best[key][0] - 1e-9:
                 best[key] = (cost, bn, ks)
@@ -111,7 +115,7 @@ def choose_tiling(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_
 def conv_gemm(pw: PackedWeight, a0: Tensor, nb: int, h: int, w: int, out: Tensor, *, a1: Optional[Tensor] = None,
               a2: Optional[Tensor] = None, stride: int = 1, rowvec: Optional[Tensor] = None, rowvec_ld: int = 0,
               residual: Optional[Tensor] = None, out_ld: Optional[int] = None, max_ctas: int = 0,
-              workspace: Optional[Tensor] = None) -> Tensor:
+              workspace: Optional[Tensor] = None, cta_pair: Optional[bool] = None) -> Tensor:
     """out[pix, :n_valid] = epilogue(implicit GEMM); see include/b200ldm.h::b200_conv_gemm."""
     assert a0.dtype == torch.bfloat16 and a0.is_contiguous()
     assert a0.numel() == nb * h * w * pw.c0, (a0.shape, nb, h, w, pw.c0)
@@ -137,7 +141,7 @@ def conv_gemm(pw: PackedWeight, a0: Tensor, nb: int, h: int, w: int, out: Tensor
     call("b200_conv_gemm", ptr(a0), pw.c0, ptr(a1) if pw.c1 else None, pw.c1, ptr(a2) if pw.c2 else None, pw.c2,
          nb, h, w, pw.ntaps, stride, ptr(pw.w), pw.n_pad, pw.n_valid, ptr(pw.bias), ptr(rowvec), rowvec_ld,
          ptr(residual), res_ld, ptr(out), ld, int(out_fp32), int(pw.geglu), pw.block_n, max_ctas, ksplit,
-         ptr(workspace) if ksplit > 1 else None, stream(), info=info)
+         ptr(workspace) if ksplit > 1 else None, int(CTA_PAIR if cta_pair is None else cta_pair), stream(), info=info)
     return out
 
 

@@ -38,14 +38,16 @@ const char* b200_last_error(void);
  * stride == 2 keeps only even (h, w) pixels (Downsample2D).  out is bf16 or fp32, leading dim out_ld.
  * ksplit > 1 (small-M, long-K layers): K is split over ksplit CTAs per tile, fp32 partial sums go to
  * `workspace` (ksplit * nb*h*w * n_pad floats) and a second kernel reduces them in fixed order and
- * applies the epilogue (deterministic).  block_n: tile width, multiple of 64 (32 allowed for fp32 output).
+ * applies the epilogue (deterministic).  cta_pair != 0: clusters of two CTAs compute 256 x block_n tiles with
+ * tcgen05.mma.cta_group::2 (each CTA stages half of the weight tile).  block_n: tile width, multiple of 64 (32 allowed for fp32 output).
  * Replaces F.conv2d / F.linear (+ peft lora.Linear.forward, + GEGLU, + residual adds) under
  * UNet2DConditionModel.forward: /root/reference/script/train/train_audioldm_lora.py:539-546,
  * /root/reference/script/inference/generate_audio.py:47-52 (LoRA config :21-29), /root/reference/app.py:14. */
 int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, const void* a2, int c2, int nb, int h, int w,
                    int ntaps, int stride, const void* wpacked, int n_pad, int n_valid, const float* bias,
                    const float* rowvec, int rowvec_ld, const void* residual, int res_ld, void* out, int out_ld,
-                   int out_fp32, int geglu, int block_n, int max_ctas, int ksplit, float* workspace, void* stream);
+                   int out_fp32, int geglu, int block_n, int max_ctas, int ksplit, float* workspace, int cta_pair,
+                   void* stream);
 
 /* GroupNorm (+ optional SiLU) over one or two NHWC sources (cat along C is never materialised).
  * One launch: a thread-block cluster per image exchanges the group statistics through DSMEM.

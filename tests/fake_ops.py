@@ -20,7 +20,7 @@ def _store(out, val, n_valid, ld=None):
 
 
 def conv_gemm(pw, a0, nb, h, w, out, *, a1=None, a2=None, stride=1, rowvec=None, rowvec_ld=0, residual=None,
-              out_ld=None, max_ctas=0, workspace=None):
+              out_ld=None, max_ctas=0, workspace=None, cta_pair=None):
     M = nb * h * w
     x = a0.view(nb, h, w, pw.c0).float()
     cols = []
