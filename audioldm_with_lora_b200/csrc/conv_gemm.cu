@@ -36,8 +36,10 @@ static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;              // 64 bf16 = one 128B swizzle row
 static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 static constexpr int kEpiWarps = 8;
-static constexpr int kThreads = 64 + kEpiWarps * 32;    // warp0 TMA, warp1 MMA, warps2-9 epilogue
+static constexpr int kThreads = 96 + kEpiWarps * 32;    // warp0 TMA(A), warp1 MMA, warps2-9 epilogue, warp10 TMA(B)
+static constexpr int kProducerBWarp = 2 + kEpiWarps;
 static constexpr int kEpiStageBytes = 32 * 128;         // per-warp staging: 32 rows x 64 bf16
+static constexpr int kEpiVecBytes = 128 * 4;            // per-warp bias(+rowvec) vector of the current chunk
 static constexpr int kSmemLimit = 227 * 1024;
 
 struct ConvGemmParams {
@@ -66,6 +68,8 @@ struct ConvGemmParams {
   int ksplit;                       // > 1: split-K; work item = (split, m_tile, n_tile), fp32 partials to `out`
   int kb_per_split;
   size_t split_stride;              // elements between the partial-sum planes
+  int debug;                        // profiling knobs (env B200_GEMM_DEBUG): 1 = no TMA after the first fill of each
+                                    // stage, 2 = no MMA (results are garbage; timing experiments only)
 };
 
 // exact-erf GELU to ~2e-7 absolute (Abramowitz-Stegun 7.1.26 erfc; bf16 output rounding is 4e-3 relative):
@@ -80,6 +84,13 @@ __device__ __forceinline__ float gelu_erf(float g) {
   const float e = poly * t * __expf(-z * z);
   return g >= 0.f ? g * fmaf(-0.5f, e, 1.0f) : 0.5f * g * e;
 }
+
+// debug timeline (B200_GEMM_DEBUG & 4): SM cycle counter of CTA 0 at fixed points of the kernel
+__device__ unsigned long long g_timeline[32];
+#define TL(i)                                                        \
+  do {                                                               \
+    if ((p.debug & 4) && blockIdx.x == 0) g_timeline[i] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ void add8(float (&v)[8], const float* src) {
   const float4 b0 = *reinterpret_cast<const float4*>(src);
@@ -100,7 +111,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int b_rows = kCta2 ? p.block_n / 2 : p.block_n;           // weight rows this CTA stages per k-block
   const int stage_bytes = kABytes + b_rows * kBlockK * 2;
   uint8_t* epi_smem = smem + p.stages * stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * kEpiStageBytes);
+  float* epi_vec = reinterpret_cast<float*>(epi_smem + kEpiWarps * kEpiStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * (kEpiStageBytes + kEpiVecBytes));
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -108,6 +120,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TL(0);
   const int num_tiles = p.num_m_groups * p.num_n_tiles * p.ksplit;  // work items of a CTA (1-CTA) / a pair (2-CTA)
   const int tile0 = kCta2 ? blockIdx.x >> 1 : blockIdx.x;
   const int tile_step = kCta2 ? gridDim.x >> 1 : gridDim.x;
@@ -117,7 +130,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmB);
     if (p.tma_out) tma_prefetch_desc(&tmOut);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);          // one arrive.expect_tx from each of the two producer threads (A, B)
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -140,13 +153,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TL(1);
   // PDL: everything above overlapped the previous kernel's tail; from here on we touch its outputs.
   pdl_launch_dependents();
   pdl_wait();
+  if (threadIdx.x == 0) TL(2);
 
-  if (warp == 0) {
-    // ================================================================ TMA producer
+  if (warp == 0 || warp == kProducerBWarp) {
+    // ================================================================ TMA producers
+    // Two threads in different warps: one streams the activation boxes (A), the other the weight tiles (B).
+    // A cp.async.bulk.tensor occupies its issuing thread for ~250 cycles; split, the two streams overlap.
     if (lane == 0) {
+      const bool do_a = warp == 0;
+      const uint32_t a_bytes = kABytes, b_bytes = static_cast<uint32_t>(b_rows) * kBlockK * 2;
       int s = 0;
       uint32_t ph = 0;
       for (int t = tile0; t < num_tiles; t += tile_step) {
@@ -163,33 +182,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* a_dst = smem + s * stage_bytes;
           uint8_t* b_dst = a_dst + kABytes;
-          // 2-CTA: both CTAs' loads are credited to the leader's barrier, which expects the pair's bytes
-          if (!kCta2) mbar_expect_tx(&full_bar[s], stage_bytes);
-          else if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * stage_bytes);
-          int c0, c1 = 0, c2 = h0;
-          const CUtensorMap* tm;
-          if (kb < p.seg_end0) {
-            const int tap = kb / p.cb0;
-            const int cb = kb - tap * p.cb0;
-            if (p.ntaps == 9) {
-              c2 = h0 + tap / 3 - 1;
-              c1 = tap % 3 - 1;
-            }
-            c0 = cb * kBlockK;
-            tm = &tmA0;
-          } else if (kb < p.seg_end1) {
-            c0 = (kb - p.seg_end0) * kBlockK;
-            tm = &tmA1;
-          } else {
-            c0 = (kb - p.seg_end1) * kBlockK;
-            tm = &tmA2;
+          if ((p.debug & 1) && ph) {                       // timing experiment: operands stay whatever is in smem
+            if (cta_rank == 0) mbar_arrive(&full_bar[s]);
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+            continue;
           }
-          if (kCta2) {
-            tma_load_4d_cta2(a_dst, tm, &full_bar[s], c0, c1, c2, n0);
-            tma_load_2d_cta2(b_dst, &tmB, &full_bar[s], kb * kBlockK, b_row0);
+          // 2-CTA: both CTAs' loads are credited to the leader's barrier, which expects the pair's bytes
+          const uint32_t my_bytes = do_a ? a_bytes : b_bytes;
+          if (!kCta2) mbar_expect_tx(&full_bar[s], my_bytes);
+          else if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * my_bytes);
+          if (do_a) {
+            int c0, c1 = 0, c2 = h0;
+            const CUtensorMap* tm;
+            if (kb < p.seg_end0) {
+              const int tap = kb / p.cb0;
+              const int cb = kb - tap * p.cb0;
+              if (p.ntaps == 9) {
+                c2 = h0 + tap / 3 - 1;
+                c1 = tap % 3 - 1;
+              }
+              c0 = cb * kBlockK;
+              tm = &tmA0;
+            } else if (kb < p.seg_end1) {
+              c0 = (kb - p.seg_end0) * kBlockK;
+              tm = &tmA1;
+            } else {
+              c0 = (kb - p.seg_end1) * kBlockK;
+              tm = &tmA2;
+            }
+            if (kCta2) tma_load_4d_cta2(a_dst, tm, &full_bar[s], c0, c1, c2, n0);
+            else tma_load_4d(a_dst, tm, &full_bar[s], c0, c1, c2, n0);
+            if (kb == kb_begin) TL(3);
+            if (kb == kb_begin + p.stages - 1) TL(4);
           } else {
-            tma_load_4d(a_dst, tm, &full_bar[s], c0, c1, c2, n0);
-            tma_load_2d(b_dst, &tmB, &full_bar[s], kb * kBlockK, b_row0);
+            if (kCta2) tma_load_2d_cta2(b_dst, &tmB, &full_bar[s], kb * kBlockK, b_row0);
+            else tma_load_2d(b_dst, &tmB, &full_bar[s], kb * kBlockK, b_row0);
           }
           if (++s == p.stages) {
             s = 0;
@@ -216,6 +243,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[s], ph);
+          if (kb == kb_begin) TL(6);
+          if (kb == kb_begin + 1) TL(7);
+          if (kb == kb_begin + 17) TL(8);
+          if (kb == kb_end - 1) TL(9);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
           const uint32_t b_addr = a_addr + kABytes;
@@ -224,6 +255,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const uint64_t b_desc = make_smem_desc(b_addr, 16, 1024, SWZ_128B);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
+            if (p.debug & 2) break;
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
             if (kCta2) umma_bf16_ss_cta2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
             else umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
@@ -237,6 +269,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         if (kCta2) umma_commit_cta2(&tfull_bar[buf], 3);     // both CTAs' epilogues own 128 rows each
         else umma_commit(&tfull_bar[buf]);
+        TL(10);
       }
     }
   } else {
@@ -255,6 +288,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const uint32_t stage_row = smem_u32(stage) + lane * 128;
     const int half = p.block_n / 2;
     const int out_cols = p.geglu ? half : p.block_n;     // output columns per tile
+    float* my_vec = epi_vec + (warp - 2) * (kEpiVecBytes / 4);
+    const bool rv_uniform = p.W * p.BH >= 32;            // the warp's 32 rows lie in one image
     int it = 0;
     for (int t = tile0; t < num_tiles; t += tile_step, ++it) {
       const int buf = it & 1;
@@ -267,20 +302,55 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int n_t = (m_tile / p.tiles_h) * p.BNI;
       const int h = h_t + hl;
       const int n = n_t + nl;
+      const int n_warp = n_t + q_n;                        // image of the warp's rows (when rv_uniform)
       bool row_ok = (h < p.H) && (n < p.NB);
       size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + wl;
       if (p.stride == 2) {
         row_ok = row_ok && ((h & 1) == 0) && ((wl & 1) == 0);
         pix = (static_cast<size_t>(n) * p.Hout + (h >> 1)) * p.Wout + (wl >> 1);
       }
-      mbar_wait(&tfull_bar[buf], use & 1);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * p.block_n;
+      const int nchunks = p.tma_out ? (out_cols >> 6) : 0;
+      // Per-chunk additive vector (bias + this image's embedding row) goes through a per-warp smem buffer and
+      // the residual row segment through registers; both are fetched BEFORE the accumulator is waited for.
+      float2 vec_a = make_float2(0.f, 0.f), vec_b = make_float2(0.f, 0.f);
+      uint4 res[8];
+      auto prefetch = [&](int cc) {
+        const int gcol = n_tile * out_cols + cc * 64 + 2 * lane;          // this lane's two columns of the chunk
+        vec_a = make_float2(0.f, 0.f);
+        vec_b = make_float2(0.f, 0.f);
+        if (!p.geglu) {
+          if (p.bias) vec_a = *reinterpret_cast<const float2*>(p.bias + gcol);
+          if (p.rowvec && rv_uniform && gcol < p.n_valid && n_warp < p.NB) {
+            const float2 rv = *reinterpret_cast<const float2*>(p.rowvec + static_cast<size_t>(n_warp) * p.rowvec_ld + gcol);
+            vec_a.x += rv.x;
+            vec_a.y += rv.y;
+          }
+        } else if (p.bias) {
+          const int bcol = n_tile * p.block_n + cc * 64 + 2 * lane;
+          vec_a = *reinterpret_cast<const float2*>(p.bias + bcol);
+          vec_b = *reinterpret_cast<const float2*>(p.bias + bcol + half);
+        }
+        if (p.residual && row_ok) {
+          const __nv_bfloat16* rp = p.residual + pix * p.res_ld + n_tile * out_cols + cc * 64;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            res[g] = (n_tile * out_cols + cc * 64 + g * 8 < p.n_valid) ? *reinterpret_cast<const uint4*>(rp + g * 8)
+                                                                        : make_uint4(0, 0, 0, 0);
+        }
+      };
+      if (hf < nchunks) prefetch(hf);
+      mbar_wait(&tfull_bar[buf], use & 1);
+      if (warp == 2 && lane == 0) TL(12);
+      tc_fence_after();
 
       if (p.tma_out) {
         // -------- bf16, stride 1: 64-column chunks -> swizzled smem -> TMA store
-        const int nchunks = out_cols >> 6;
         for (int cc = hf; cc < nchunks; cc += 2) {
+          __syncwarp();                                     // previous chunk's readers of my_vec are done
+          *reinterpret_cast<float2*>(my_vec + 2 * lane) = vec_a;
+          if (p.geglu) *reinterpret_cast<float2*>(my_vec + 64 + 2 * lane) = vec_b;
+          __syncwarp();
           uint32_t pk[32];
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
@@ -295,12 +365,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+                add8(v, my_vec + hh * 32 + g * 8);
                 const int cg = gcol + g * 8;
-                if (p.bias) add8(v, p.bias + cg);
                 if (row_ok && cg < p.n_valid) {
-                  if (p.rowvec) add8(v, p.rowvec + static_cast<size_t>(n) * p.rowvec_ld + cg);
+                  if (p.rowvec && !rv_uniform) add8(v, p.rowvec + static_cast<size_t>(n) * p.rowvec_ld + cg);
                   if (p.residual) {
-                    const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + pix * p.res_ld + cg);
+                    const uint4 rr = res[hh * 4 + g];
                     v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
                     v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
                   }
@@ -314,7 +384,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               tmem_ld_x32(t_row + oc, r);
               tmem_ld_x32(t_row + half + oc, rg);
               tmem_wait_ld();
-              const int bcol = n_tile * p.block_n + oc;
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 float v[8], gt[8];
@@ -323,10 +392,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                   v[j] = __uint_as_float(r[g * 8 + j]);
                   gt[j] = __uint_as_float(rg[g * 8 + j]);
                 }
-                if (p.bias) {
-                  add8(v, p.bias + bcol + g * 8);
-                  add8(gt, p.bias + bcol + half + g * 8);
-                }
+                add8(v, my_vec + hh * 32 + g * 8);
+                add8(gt, my_vec + 64 + hh * 32 + g * 8);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] *= gelu_erf(gt[j]);
 #pragma unroll
@@ -334,6 +401,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               }
             }
           }
+          if (cc + 2 < nchunks) prefetch(cc + 2);          // next chunk's vector / residual while this one is stored
           // the previous TMA store of this warp must have finished reading the staging tile
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
@@ -390,6 +458,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
         }
       }
+      if (warp == 2 && lane == 0) TL(13);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -397,8 +466,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         else mbar_arrive(&tempty_bar[buf]);
       }
     }
-    if (p.tma_out && lane == 0) tma_store_wait_all<0>();
+    // smem may not be released while a bulk store still reads it; global visibility comes with grid completion
+    if (p.tma_out && lane == 0) tma_store_wait_read<0>();
+    if (warp == 2 && lane == 0) TL(14);
   }
+  if (warp == 0 && lane == 0) TL(5);
 
   tc_fence_before();
   if (kCta2) cluster_sync_all();      // nobody exits while the peer may still signal its barriers / read its smem
@@ -408,6 +480,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (kCta2) tmem_dealloc2(tmem_base, p.tmem_cols);
     else tmem_dealloc(tmem_base, p.tmem_cols);
   }
+  if (threadIdx.x == 32) TL(15);
 }
 
 // Split-K second stage: out[pix, n] = sum_s ws[s][pix][n] (fixed order) + bias + rowvec[image] + residual -> bf16.
@@ -460,6 +533,13 @@ static int pick_box(int H, int W, int NB, int* BH, int* BNI) {
 }  // namespace b200
 
 using namespace b200;
+
+// Debug only (not part of the product API surface beyond the header note): copy the CTA-0 timeline out.
+extern "C" int b200_debug_timeline(unsigned long long* host_out, int n) {
+  if (n > 32) n = 32;
+  cudaError_t e = cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * n);
+  return e == cudaSuccess ? B200_OK : fail(B200_ERR_CUDA, "debug_timeline: %s", cudaGetErrorString(e));
+}
 
 // C-ABI: see include/b200ldm.h
 extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, const void* a2, int c2, int nb, int h,
@@ -523,9 +603,13 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
   p.num_m_groups = cta2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
   const int b_rows = cta2 ? block_n / 2 : block_n;
   const int stage_bytes = kABytes + b_rows * kBlockK * 2;
-  const int fixed = kEpiWarps * kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  const int fixed = kEpiWarps * (kEpiStageBytes + kEpiVecBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
   p.stages = (kSmemLimit - fixed) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
+  static const int dbg_stages = getenv("B200_GEMM_STAGES") ? atoi(getenv("B200_GEMM_STAGES")) : 0;
+  static const int dbg_flags = getenv("B200_GEMM_DEBUG") ? atoi(getenv("B200_GEMM_DEBUG")) : 0;
+  if (dbg_stages > 0 && dbg_stages < p.stages) p.stages = dbg_stages;
+  p.debug = dbg_flags;
   const int smem_bytes = p.stages * stage_bytes + fixed;
 
   CUtensorMap tA[3], tB, tO;

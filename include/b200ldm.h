@@ -27,6 +27,10 @@ extern "C" {
 
 int b200_version(void);
 const char* b200_last_error(void);
+/* Profiling aid: with env B200_GEMM_DEBUG=4 b200_conv_gemm's CTA 0 records its SM cycle counter at fixed
+ * points (kernel entry, after the prologue, first operands landed, last MMA committed, epilogue done, exit);
+ * this copies the first n (<= 32) records of the most recent launch to host memory. */
+int b200_debug_timeline(unsigned long long* host_out, int n);
 
 /* Implicit-GEMM convolution / linear layer on tcgen05 tensor cores (TMA-fed, TMEM accumulator).
  *   out[pix, n] = epi( sum_seg sum_tap sum_c A_seg[pix @ tap, c] * wpacked[n, k(seg,tap,c)] )

@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""CTA-0 cycle timeline of one b200_conv_gemm launch (run with B200_GEMM_DEBUG=4)."""
+import ctypes
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from audioldm_with_lora_b200 import _lib, ops, packing  # noqa: E402
+
+NAMES = {0: "entry", 1: "prologue done", 2: "pdl_wait done", 3: "producer: 1st TMA issued", 4: "producer: stages filled",
+         5: "producer: done", 6: "mma: 1st full", 7: "mma: 2nd full", 8: "mma: kb 17", 9: "mma: last full", 10: "mma: tfull commit",
+         12: "epi: tfull seen", 13: "epi: tile done", 14: "epi: stores complete", 15: "exit"}
+g = torch.Generator().manual_seed(0)
+cases = [("conv L1 256->256", 16, 125, 8, 256, 256, 9), ("lin L3 640->640", 1, 1024, 1, 640, 640, 1),
+         ("lin L1 qkv", 1, 16000, 1, 320, 768, 1), ("conv L0 128", 16, 250, 16, 128, 128, 9)]
+for label, nb, hh, ww, ci, co, taps in cases:
+    x = torch.randn(nb * hh * ww, ci, generator=g).to("cuda", torch.bfloat16)
+    wt = torch.randn(co, taps * ci, generator=g) * (taps * ci) ** -0.5
+    out = torch.empty(nb * hh * ww, co, dtype=torch.bfloat16, device="cuda")
+    bn = ops.choose_block_n(co, ops.num_m_tiles(nb, hh, ww))
+    pw = packing.pack([wt], torch.zeros(co), bn, taps, ci, device="cuda")
+    for _ in range(3):
+        ops.conv_gemm(pw, x, nb, hh, ww, out)
+    torch.cuda.synchronize()
+    buf = (ctypes.c_ulonglong * 32)()
+    _lib.check(_lib.load().b200_debug_timeline(ctypes.cast(buf, ctypes.c_void_p), 32), "timeline")
+    t0 = buf[0]
+    print(f"== {label} bn={bn}")
+    for i in sorted(NAMES):
+        if buf[i]:
+            print(f"   {NAMES[i]:<28} +{buf[i] - t0:>7} cyc")
