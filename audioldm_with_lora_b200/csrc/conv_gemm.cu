@@ -68,6 +68,7 @@ struct ConvGemmParams {
   int ksplit;                       // > 1: split-K; work item = (split, m_tile, n_tile), fp32 partials to `out`
   int kb_per_split;
   size_t split_stride;              // elements between the partial-sum planes
+  int a_rank2;                      // linear layers (W = 1, one image): A tensor maps are plain 2-D [rows, K]
   int debug;                        // profiling knobs (env B200_GEMM_DEBUG): 1 = no TMA after the first fill of each
                                     // stage, 2 = no MMA (results are garbage; timing experiments only)
 };
@@ -162,12 +163,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 0 || warp == kProducerBWarp) {
     // ================================================================ TMA producers
     // Two threads in different warps: one streams the activation boxes (A), the other the weight tiles (B).
-    // A cp.async.bulk.tensor occupies its issuing thread for ~250 cycles; split, the two streams overlap.
+    // These are single-thread scalar loops, i.e. every instruction costs its full latency: k-block coordinates
+    // advance incrementally (no divisions) and the poll of the NEXT stage's empty barrier is issued before the
+    // current stage's TMA so that its latency is hidden.
     if (lane == 0) {
       const bool do_a = warp == 0;
-      const uint32_t a_bytes = kABytes, b_bytes = static_cast<uint32_t>(b_rows) * kBlockK * 2;
+      const uint32_t my_bytes = (do_a ? static_cast<uint32_t>(kABytes) : static_cast<uint32_t>(b_rows) * kBlockK * 2) *
+                                (kCta2 ? 2u : 1u);       // 2-CTA: the leader's barrier expects the pair's bytes
+      const bool expect = !kCta2 || cta_rank == 0;
+      uint8_t* const dst0 = smem + (do_a ? 0 : kABytes);
       int s = 0;
       uint32_t ph = 0;
+      bool ready = true;                                  // fresh barriers: the first pass over the stages never waits
+      long fills = 0;
       for (int t = tile0; t < num_tiles; t += tile_step) {
         const int n_tile = t % p.num_n_tiles;
         const int m_group = (t / p.num_n_tiles) % p.num_m_groups;
@@ -178,59 +186,72 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int h0 = (m_tile % p.tiles_h) * p.BH;
         const int n0 = (m_tile / p.tiles_h) * p.BNI;
         const int b_row0 = n_tile * p.block_n + static_cast<int>(cta_rank) * b_rows;
+        // incremental (segment, tap, channel-block) state of k-block kb_begin
+        int seg = kb_begin < p.seg_end0 ? 0 : (kb_begin < p.seg_end1 ? 1 : 2);
+        int tap = 0, cb = 0;
+        if (seg == 0) { tap = kb_begin / p.cb0; cb = kb_begin - tap * p.cb0; }
+        else cb = kb_begin - (seg == 1 ? p.seg_end0 : p.seg_end1);
+        int dh = 0, dw = 0;
+        if (seg == 0 && p.ntaps == 9) { dh = tap / 3 - 1; dw = tap - (tap / 3) * 3 - 1; }
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* a_dst = smem + s * stage_bytes;
-          uint8_t* b_dst = a_dst + kABytes;
+          if (!ready) mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* dst = dst0 + s * stage_bytes;
+          uint64_t* fb = &full_bar[s];
+          // look ahead: poll the next stage's empty barrier now, use the answer next iteration
+          int s_next = s + 1;
+          uint32_t ph_next = ph;
+          if (s_next == p.stages) { s_next = 0; ph_next ^= 1; }
+          ++fills;
+          ready = (fills < p.stages) ? true : mbar_try_wait(&empty_bar[s_next], ph_next ^ 1);
           if ((p.debug & 1) && ph) {                       // timing experiment: operands stay whatever is in smem
-            if (cta_rank == 0) mbar_arrive(&full_bar[s]);
-            if (++s == p.stages) { s = 0; ph ^= 1; }
-            continue;
-          }
-          // 2-CTA: both CTAs' loads are credited to the leader's barrier, which expects the pair's bytes
-          const uint32_t my_bytes = do_a ? a_bytes : b_bytes;
-          if (!kCta2) mbar_expect_tx(&full_bar[s], my_bytes);
-          else if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * my_bytes);
-          if (do_a) {
-            int c0, c1 = 0, c2 = h0;
-            const CUtensorMap* tm;
-            if (kb < p.seg_end0) {
-              const int tap = kb / p.cb0;
-              const int cb = kb - tap * p.cb0;
-              if (p.ntaps == 9) {
-                c2 = h0 + tap / 3 - 1;
-                c1 = tap % 3 - 1;
-              }
-              c0 = cb * kBlockK;
-              tm = &tmA0;
-            } else if (kb < p.seg_end1) {
-              c0 = (kb - p.seg_end0) * kBlockK;
-              tm = &tmA1;
-            } else {
-              c0 = (kb - p.seg_end1) * kBlockK;
-              tm = &tmA2;
-            }
-            if (kCta2) tma_load_4d_cta2(a_dst, tm, &full_bar[s], c0, c1, c2, n0);
-            else tma_load_4d(a_dst, tm, &full_bar[s], c0, c1, c2, n0);
-            if (kb == kb_begin) TL(3);
-            if (kb == kb_begin + p.stages - 1) TL(4);
+            if (cta_rank == 0) mbar_arrive(fb);
           } else {
-            if (kCta2) tma_load_2d_cta2(b_dst, &tmB, &full_bar[s], kb * kBlockK, b_row0);
-            else tma_load_2d(b_dst, &tmB, &full_bar[s], kb * kBlockK, b_row0);
+            if (expect) mbar_expect_tx(fb, my_bytes);
+            if (do_a) {
+              const CUtensorMap* tm = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : &tmA2);
+              if (p.a_rank2) {
+                if (kCta2) tma_load_2d_cta2(dst, tm, fb, cb * kBlockK, h0);
+                else tma_load_2d(dst, tm, fb, cb * kBlockK, h0);
+              } else {
+                if (kCta2) tma_load_4d_cta2(dst, tm, fb, cb * kBlockK, dw, h0 + dh, n0);
+                else tma_load_4d(dst, tm, fb, cb * kBlockK, dw, h0 + dh, n0);
+              }
+            } else {
+              if (kCta2) tma_load_2d_cta2(dst, &tmB, fb, kb * kBlockK, b_row0);
+              else tma_load_2d(dst, &tmB, fb, kb * kBlockK, b_row0);
+            }
           }
-          if (++s == p.stages) {
-            s = 0;
-            ph ^= 1;
+          // advance the k-block state
+          ++cb;
+          if (seg == 0) {
+            if (cb == p.cb0) {
+              cb = 0;
+              if (++tap == p.ntaps) { seg = 1; dh = 0; dw = 0; if (p.seg_end1 == p.seg_end0) seg = 2; }
+              else if (++dw == 2) { dw = -1; ++dh; }
+            }
+          } else if (seg == 1 && kb + 1 == p.seg_end1) {
+            seg = 2;
+            cb = 0;
           }
+          s = s_next;
+          ph = ph_next;
         }
       }
+      if (do_a) TL(5);
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (one thread)
+    // ================================================================ MMA issuer (one thread, leader CTA only)
     if (lane == 0 && cta_rank == 0) {
       const uint32_t idesc = make_idesc_bf16(kCta2 ? 2 * kBlockM : kBlockM, p.block_n, 0, 0);
+      // K-major, 128B swizzle: 8-row atom = 1024 B -> SBO = 1024; LBO unused (1).  Stage s adds s * stage_bytes.
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(smem), 16, 1024, SWZ_128B);
+      const uint64_t b_desc0 = make_smem_desc(smem_u32(smem) + kABytes, 16, 1024, SWZ_128B);
+      const uint64_t desc_step = static_cast<uint64_t>(stage_bytes >> 4);
+      uint64_t a_desc = a_desc0, b_desc = b_desc0;
       int s = 0;
       uint32_t ph = 0;
+      bool ready = false;
+      bool polled = false;
       int it = 0;
       for (int t = tile0; t < num_tiles; t += tile_step, ++it) {
         const int buf = it & 1;
@@ -241,35 +262,45 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int split = t / (p.num_n_tiles * p.num_m_groups);
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+        if (it == 0) TL(6);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&full_bar[s], ph);
-          if (kb == kb_begin) TL(6);
-          if (kb == kb_begin + 1) TL(7);
-          if (kb == kb_begin + 17) TL(8);
-          if (kb == kb_end - 1) TL(9);
+          if (!(polled && ready)) mbar_wait(&full_bar[s], ph);
+          // look ahead: poll the next stage's full barrier now, use the answer next iteration
+          int s_next = s + 1;
+          uint32_t ph_next = ph;
+          if (s_next == p.stages) { s_next = 0; ph_next ^= 1; }
+          ready = mbar_try_wait(&full_bar[s_next], ph_next);
+          polled = true;
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint32_t b_addr = a_addr + kABytes;
-          // K-major, 128B swizzle: 8-row atom = 1024 B -> SBO = 1024; LBO unused (1).
-          const uint64_t a_desc = make_smem_desc(a_addr, 16, 1024, SWZ_128B);
-          const uint64_t b_desc = make_smem_desc(b_addr, 16, 1024, SWZ_128B);
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            if (p.debug & 2) break;
+          if (!(p.debug & 2)) {
+            const uint32_t acc0 = kb != kb_begin;
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
-            if (kCta2) umma_bf16_ss_cta2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
-            else umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
+            if (kCta2) {
+              umma_bf16_ss_cta2(d_tmem, a_desc, b_desc, idesc, acc0);
+              umma_bf16_ss_cta2(d_tmem, a_desc + 2, b_desc + 2, idesc, 1);
+              umma_bf16_ss_cta2(d_tmem, a_desc + 4, b_desc + 4, idesc, 1);
+              umma_bf16_ss_cta2(d_tmem, a_desc + 6, b_desc + 6, idesc, 1);
+              umma_commit_cta2(&empty_bar[s], 3);          // frees the stage in both CTAs
+            } else {
+              umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, acc0);
+              umma_bf16_ss(d_tmem, a_desc + 2, b_desc + 2, idesc, 1);
+              umma_bf16_ss(d_tmem, a_desc + 4, b_desc + 4, idesc, 1);
+              umma_bf16_ss(d_tmem, a_desc + 6, b_desc + 6, idesc, 1);
+              umma_commit(&empty_bar[s]);
+            }
+          } else {
+            if (kCta2) umma_commit_cta2(&empty_bar[s], 3);
+            else umma_commit(&empty_bar[s]);
           }
-          if (kCta2) umma_commit_cta2(&empty_bar[s], 3);     // frees the stage in both CTAs
-          else umma_commit(&empty_bar[s]);
-          if (++s == p.stages) {
-            s = 0;
-            ph ^= 1;
-          }
+          a_desc += desc_step;
+          b_desc += desc_step;
+          if (s_next == 0) { a_desc = a_desc0; b_desc = b_desc0; }
+          s = s_next;
+          ph = ph_next;
         }
         if (kCta2) umma_commit_cta2(&tfull_bar[buf], 3);     // both CTAs' epilogues own 128 rows each
         else umma_commit(&tfull_bar[buf]);
-        TL(10);
+        if (it == 0) TL(10);
       }
     }
   } else {
@@ -615,12 +646,22 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
   CUtensorMap tA[3], tB, tO;
   const void* srcs[3] = {a0, a1 ? a1 : a0, a2 ? a2 : a0};
   const int chans[3] = {c0, c1 ? c1 : c0, c2 ? c2 : c0};
+  static const bool no_rank2 = getenv("B200_GEMM_NO_RANK2") != nullptr;   // debugging knob
+  p.a_rank2 = (ntaps == 1 && w == 1 && nb == 1 && !no_rank2) ? 1 : 0;
   for (int i = 0; i < 3; ++i) {
     const uint64_t C = chans[i];
-    uint64_t dims[4] = {C, (uint64_t)w, (uint64_t)h, (uint64_t)nb};
-    uint64_t strides[3] = {C, C * w, C * w * h};
-    uint32_t box[4] = {64, (uint32_t)w, (uint32_t)p.BH, (uint32_t)p.BNI};
-    int rc = make_tmap_bf16(&tA[i], srcs[i], 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc;
+    if (p.a_rank2) {
+      uint64_t dims[2] = {C, (uint64_t)h};
+      uint64_t strides[1] = {C};
+      uint32_t box[2] = {64, 128};
+      rc = make_tmap_bf16(&tA[i], srcs[i], 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    } else {
+      uint64_t dims[4] = {C, (uint64_t)w, (uint64_t)h, (uint64_t)nb};
+      uint64_t strides[3] = {C, C * w, C * w * h};
+      uint32_t box[4] = {64, (uint32_t)w, (uint32_t)p.BH, (uint32_t)p.BNI};
+      rc = make_tmap_bf16(&tA[i], srcs[i], 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
     if (rc) return rc;
   }
   {

@@ -11,10 +11,11 @@ from audioldm_with_lora_b200 import _lib, ops, packing  # noqa: E402
 
 NAMES = {0: "entry", 1: "prologue done", 2: "pdl_wait done", 3: "producer: 1st TMA issued", 4: "producer: stages filled",
          5: "producer: done", 6: "mma: 1st full", 7: "mma: 2nd full", 8: "mma: kb 17", 9: "mma: last full", 10: "mma: tfull commit",
-         12: "epi: tfull seen", 13: "epi: tile done", 14: "epi: stores complete", 15: "exit"}
+         16: "mma kb9: before wait", 17: "mma kb9: after wait", 18: "mma kb9: 4 MMAs issued", 19: "mma kb9: committed",
+         20: "mma kb10: committed", 21: "prodA kb9: before wait", 22: "prodA kb9: after wait", 23: "prodA kb9: issued",
+         24: "prodA kb10: issued", 12: "epi: tfull seen", 13: "epi: tile done", 14: "epi: stores complete", 15: "exit"}
 g = torch.Generator().manual_seed(0)
-cases = [("conv L1 256->256", 16, 125, 8, 256, 256, 9), ("lin L3 640->640", 1, 1024, 1, 640, 640, 1),
-         ("lin L1 qkv", 1, 16000, 1, 320, 768, 1), ("conv L0 128", 16, 250, 16, 128, 128, 9)]
+cases = [("conv L1 256->256", 16, 125, 8, 256, 256, 9), ("lin L3 640->640", 1, 1024, 1, 640, 640, 1)]
 for label, nb, hh, ww, ci, co, taps in cases:
     x = torch.randn(nb * hh * ww, ci, generator=g).to("cuda", torch.bfloat16)
     wt = torch.randn(co, taps * ci, generator=g) * (taps * ci) ** -0.5
