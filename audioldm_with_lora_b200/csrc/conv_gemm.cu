@@ -202,7 +202,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           uint32_t ph_next = ph;
           if (s_next == p.stages) { s_next = 0; ph_next ^= 1; }
           ++fills;
-          ready = (fills < p.stages) ? true : mbar_try_wait(&empty_bar[s_next], ph_next ^ 1);
+          ready = (fills < p.stages) ? true : mbar_test_wait(&empty_bar[s_next], ph_next ^ 1);
           if ((p.debug & 1) && ph) {                       // timing experiment: operands stay whatever is in smem
             if (cta_rank == 0) mbar_arrive(fb);
           } else {
@@ -269,7 +269,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           int s_next = s + 1;
           uint32_t ph_next = ph;
           if (s_next == p.stages) { s_next = 0; ph_next ^= 1; }
-          ready = mbar_try_wait(&full_bar[s_next], ph_next);
+          ready = mbar_test_wait(&full_bar[s_next], ph_next);
           polled = true;
           tc_fence_after();
           if (!(p.debug & 2)) {
