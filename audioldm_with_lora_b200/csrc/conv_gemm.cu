@@ -101,7 +101,7 @@ __device__ __forceinline__ void add8(float (&v)[8], const float* src) {
 }
 
 template <bool kCta2>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(184)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const ConvGemmParams p) {
@@ -263,15 +263,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
         if (it == 0) TL(6);
+        long long acc_wait = 0, acc_test = 0, acc_fence = 0, acc_mma = 0, acc_rest = 0, n_blocked = 0, tq = 0;
+        const bool prof = (p.debug & 8) && blockIdx.x == 0;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          if (!(polled && ready)) mbar_wait(&full_bar[s], ph);
+          if (prof) tq = clock64();
+          if (!(polled && ready)) { mbar_wait(&full_bar[s], ph); ++n_blocked; }
+          if (prof) { const long long now = clock64(); acc_wait += now - tq; tq = now; }
           // look ahead: poll the next stage's full barrier now, use the answer next iteration
           int s_next = s + 1;
           uint32_t ph_next = ph;
           if (s_next == p.stages) { s_next = 0; ph_next ^= 1; }
           ready = mbar_test_wait(&full_bar[s_next], ph_next);
           polled = true;
+          if (prof) { const long long now = clock64(); acc_test += now - tq; tq = now; }
           tc_fence_after();
+          if (prof) { const long long now = clock64(); acc_fence += now - tq; tq = now; }
           if (!(p.debug & 2)) {
             const uint32_t acc0 = kb != kb_begin;
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
@@ -292,11 +298,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (kCta2) umma_commit_cta2(&empty_bar[s], 3);
             else umma_commit(&empty_bar[s]);
           }
+          if (prof) { const long long now = clock64(); acc_mma += now - tq; tq = now; }
           a_desc += desc_step;
           b_desc += desc_step;
           if (s_next == 0) { a_desc = a_desc0; b_desc = b_desc0; }
           s = s_next;
           ph = ph_next;
+          if (prof) { const long long now = clock64(); acc_rest += now - tq; tq = now; }
+        }
+        if (prof && it == 0) {
+          g_timeline[25] = acc_wait; g_timeline[26] = acc_test; g_timeline[27] = acc_fence; g_timeline[28] = acc_mma;
+          g_timeline[29] = acc_rest; g_timeline[30] = n_blocked; g_timeline[31] = kb_end - kb_begin;
         }
         if (kCta2) umma_commit_cta2(&tfull_bar[buf], 3);     // both CTAs' epilogues own 128 rows each
         else umma_commit(&tfull_bar[buf]);
@@ -383,14 +395,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (p.geglu) *reinterpret_cast<float2*>(my_vec + 64 + 2 * lane) = vec_b;
           __syncwarp();
           uint32_t pk[32];
+          uint32_t r2[2][32];
+          if (!p.geglu) {                                   // both halves of the chunk in flight, one wait
+            tmem_ld_x32(t_row + cc * 64, r2[0]);
+            tmem_ld_x32(t_row + cc * 64 + 32, r2[1]);
+            tmem_wait_ld();
+          }
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             const int oc = cc * 64 + hh * 32;              // output column inside the tile
             const int gcol = n_tile * out_cols + oc;       // global output column
-            uint32_t r[32];
+            uint32_t (&r)[32] = r2[hh];
             if (!p.geglu) {
-              tmem_ld_x32(t_row + oc, r);
-              tmem_wait_ld();
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 float v[8];
@@ -433,9 +449,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
           }
           if (cc + 2 < nchunks) prefetch(cc + 2);          // next chunk's vector / residual while this one is stored
+          if (warp == 2 && lane == 0) TL(cc == 0 ? 16 : 20);
           // the previous TMA store of this warp must have finished reading the staging tile
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
+          if (warp == 2 && lane == 0) TL(cc == 0 ? 17 : 21);
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const uint32_t addr = stage_row + ((g ^ (lane & 7)) << 4);
@@ -445,10 +463,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
           fence_proxy_async_smem();
           __syncwarp();
+          if (warp == 2 && lane == 0) TL(cc == 0 ? 18 : 22);
           if (lane == 0) {
             tma_store_4d(&tmOut, stage, n_tile * out_cols + cc * 64, q_w, h_t + q_h, n_t + q_n);
             tma_store_commit();
           }
+          if (warp == 2 && lane == 0) TL(cc == 0 ? 19 : 23);
         }
       } else {
         // -------- fp32 output and/or stride 2: direct 16-byte stores, 32-column groups
@@ -630,7 +650,8 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
   while (tc < 2 * block_n) tc *= 2;
   p.tmem_cols = tc;
   // 2-CTA pairs: needs two halves of >= 64 weight rows and more than one m-tile to pair up
-  const bool cta2 = cta_pair && block_n % 128 == 0 && p.num_m_tiles >= 2;
+  // (worth its longer prologue / cluster syncs only when the k-loop dominates)
+  const bool cta2 = cta_pair && block_n % 128 == 0 && p.num_m_tiles >= 2 && (cta_pair > 1 || p.num_kb >= 16);
   p.num_m_groups = cta2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
   const int b_rows = cta2 ? block_n / 2 : block_n;
   const int stage_bytes = kABytes + b_rows * kBlockK * 2;

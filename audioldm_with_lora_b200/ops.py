@@ -98,7 +98,7 @@ def choose_tiling(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_
         if ks > 1 and (not allow_split or geglu or num_kb < 16 * ks // 2):
             continue
         for bn in range(step, 257, step):
-            pair = CTA_PAIR and bn % 128 == 0 and m_tiles >= 2
+            pair = CTA_PAIR and bn % 128 == 0 and m_tiles >= 2 and num_kb >= 16
             tiles1 = (2 * math.ceil(m_tiles / 2) if pair else m_tiles) * math.ceil(n / bn)
             if ks > 1 and tiles1 > NUM_SMS // 2:
                 continue
@@ -141,7 +141,7 @@ def conv_gemm(pw: PackedWeight, a0: Tensor, nb: int, h: int, w: int, out: Tensor
     call("b200_conv_gemm", ptr(a0), pw.c0, ptr(a1) if pw.c1 else None, pw.c1, ptr(a2) if pw.c2 else None, pw.c2,
          nb, h, w, pw.ntaps, stride, ptr(pw.w), pw.n_pad, pw.n_valid, ptr(pw.bias), ptr(rowvec), rowvec_ld,
          ptr(residual), res_ld, ptr(out), ld, int(out_fp32), int(pw.geglu), pw.block_n, max_ctas, ksplit,
-         ptr(workspace) if ksplit > 1 else None, int(CTA_PAIR if cta_pair is None else cta_pair), stream(), info=info)
+         ptr(workspace) if ksplit > 1 else None, (int(CTA_PAIR) if cta_pair is None else (2 if cta_pair else 0)), stream(), info=info)
     return out
 
 

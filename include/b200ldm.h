@@ -42,7 +42,8 @@ int b200_debug_timeline(unsigned long long* host_out, int n);
  * stride == 2 keeps only even (h, w) pixels (Downsample2D).  out is bf16 or fp32, leading dim out_ld.
  * ksplit > 1 (small-M, long-K layers): K is split over ksplit CTAs per tile, fp32 partial sums go to
  * `workspace` (ksplit * nb*h*w * n_pad floats) and a second kernel reduces them in fixed order and
- * applies the epilogue (deterministic).  cta_pair != 0: clusters of two CTAs compute 256 x block_n tiles with
+ * applies the epilogue (deterministic).  cta_pair: 0 never, 1 when the k-loop is long enough to pay for it, 2 always (if the shape allows):
+ * clusters of two CTAs compute 256 x block_n tiles with
  * tcgen05.mma.cta_group::2 (each CTA stages half of the weight tile).  block_n: tile width, multiple of 64 (32 allowed for fp32 output).
  * Replaces F.conv2d / F.linear (+ peft lora.Linear.forward, + GEGLU, + residual adds) under
  * UNet2DConditionModel.forward: /root/reference/script/train/train_audioldm_lora.py:539-546,

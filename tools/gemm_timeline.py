@@ -11,9 +11,9 @@ from audioldm_with_lora_b200 import _lib, ops, packing  # noqa: E402
 
 NAMES = {0: "entry", 1: "prologue done", 2: "pdl_wait done", 3: "producer: 1st TMA issued", 4: "producer: stages filled",
          5: "producer: done", 6: "mma: 1st full", 7: "mma: 2nd full", 8: "mma: kb 17", 9: "mma: last full", 10: "mma: tfull commit",
-         16: "mma kb9: before wait", 17: "mma kb9: after wait", 18: "mma kb9: 4 MMAs issued", 19: "mma kb9: committed",
-         20: "mma kb10: committed", 21: "prodA kb9: before wait", 22: "prodA kb9: after wait", 23: "prodA kb9: issued",
-         24: "prodA kb10: issued", 12: "epi: tfull seen", 13: "epi: tile done", 14: "epi: stores complete", 15: "exit"}
+         16: "epi c0: math done", 17: "epi c0: staging free", 18: "epi c0: smem written", 19: "epi c0: store issued",
+         20: "epi c2: math done", 21: "epi c2: staging free", 22: "epi c2: smem written", 23: "epi c2: store issued",
+         12: "epi: tfull seen", 13: "epi: tile done", 14: "epi: stores complete", 15: "exit"}
 g = torch.Generator().manual_seed(0)
 cases = [("conv L1 256->256", 16, 125, 8, 256, 256, 9), ("lin L3 640->640", 1, 1024, 1, 640, 640, 1)]
 for label, nb, hh, ww, ci, co, taps in cases:
@@ -32,3 +32,7 @@ for label, nb, hh, ww, ci, co, taps in cases:
     for i in sorted(NAMES):
         if buf[i]:
             print(f"   {NAMES[i]:<28} +{buf[i] - t0:>7} cyc")
+    if buf[31]:
+        n = buf[31]
+        print(f"   MMA thread over {n} k-blocks: wait {buf[25] / n:.0f}  test_wait {buf[26] / n:.0f}  fence {buf[27] / n:.0f}  "
+              f"mma+commit {buf[28] / n:.0f}  rest {buf[29] / n:.0f} cyc/kb; blocked waits {buf[30]}")
