@@ -101,7 +101,7 @@ __device__ __forceinline__ void add8(float (&v)[8], const float* src) {
 }
 
 template <bool kCta2>
-__global__ void __maxnreg__(184)
+__global__ void __maxnreg__(176)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const ConvGemmParams p) {
