@@ -36,8 +36,7 @@ static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;              // 64 bf16 = one 128B swizzle row
 static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 static constexpr int kEpiWarps = 8;
-static constexpr int kThreads = 96 + kEpiWarps * 32;    // warp0 TMA(A), warp1 MMA, warps2-9 epilogue, warp10 TMA(B)
-static constexpr int kProducerBWarp = 2 + kEpiWarps;
+static constexpr int kThreads = 64 + kEpiWarps * 32;    // warp0 TMA, warp1 MMA, warps2-9 epilogue
 static constexpr int kEpiStageBytes = 32 * 128;         // per-warp staging: 32 rows x 64 bf16
 static constexpr int kEpiVecBytes = 128 * 4;            // per-warp bias(+rowvec) vector of the current chunk
 static constexpr int kSmemLimit = 227 * 1024;
@@ -101,7 +100,7 @@ __device__ __forceinline__ void add8(float (&v)[8], const float* src) {
 }
 
 template <bool kCta2>
-__global__ void __maxnreg__(176)
+__global__ void __launch_bounds__(kThreads, 1)      // 10 warps are allocated as 12: 168 registers per thread at most
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const ConvGemmParams p) {
@@ -131,7 +130,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmB);
     if (p.tma_out) tma_prefetch_desc(&tmOut);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 2);          // one arrive.expect_tx from each of the two producer threads (A, B)
+      mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -160,18 +159,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   pdl_wait();
   if (threadIdx.x == 0) TL(2);
 
-  if (warp == 0 || warp == kProducerBWarp) {
-    // ================================================================ TMA producers
-    // Two threads in different warps: one streams the activation boxes (A), the other the weight tiles (B).
-    // These are single-thread scalar loops, i.e. every instruction costs its full latency: k-block coordinates
-    // advance incrementally (no divisions) and the poll of the NEXT stage's empty barrier is issued before the
-    // current stage's TMA so that its latency is hidden.
+  if (warp == 0) {
+    // ================================================================ TMA producer (one thread)
+    // A single-thread scalar loop, i.e. every instruction costs its full latency: k-block coordinates advance
+    // incrementally (no divisions) and the poll of the NEXT stage's empty barrier is issued before the current
+    // stage's TMA so that its latency is hidden.  (Splitting A and B over two warps was measured: no gain.)
     if (lane == 0) {
-      const bool do_a = warp == 0;
-      const uint32_t my_bytes = (do_a ? static_cast<uint32_t>(kABytes) : static_cast<uint32_t>(b_rows) * kBlockK * 2) *
-                                (kCta2 ? 2u : 1u);       // 2-CTA: the leader's barrier expects the pair's bytes
+      const uint32_t my_bytes = static_cast<uint32_t>(stage_bytes) * (kCta2 ? 2u : 1u);   // 2-CTA: leader expects the pair's bytes
       const bool expect = !kCta2 || cta_rank == 0;
-      uint8_t* const dst0 = smem + (do_a ? 0 : kABytes);
       int s = 0;
       uint32_t ph = 0;
       bool ready = true;                                  // fresh barriers: the first pass over the stages never waits
@@ -195,7 +190,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (seg == 0 && p.ntaps == 9) { dh = tap / 3 - 1; dw = tap - (tap / 3) * 3 - 1; }
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           if (!ready) mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* dst = dst0 + s * stage_bytes;
+          uint8_t* dst = smem + s * stage_bytes;
           uint64_t* fb = &full_bar[s];
           // look ahead: poll the next stage's empty barrier now, use the answer next iteration
           int s_next = s + 1;
@@ -207,19 +202,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (cta_rank == 0) mbar_arrive(fb);
           } else {
             if (expect) mbar_expect_tx(fb, my_bytes);
-            if (do_a) {
-              const CUtensorMap* tm = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : &tmA2);
-              if (p.a_rank2) {
-                if (kCta2) tma_load_2d_cta2(dst, tm, fb, cb * kBlockK, h0);
-                else tma_load_2d(dst, tm, fb, cb * kBlockK, h0);
-              } else {
-                if (kCta2) tma_load_4d_cta2(dst, tm, fb, cb * kBlockK, dw, h0 + dh, n0);
-                else tma_load_4d(dst, tm, fb, cb * kBlockK, dw, h0 + dh, n0);
-              }
+            const CUtensorMap* tm = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : &tmA2);
+            if (p.a_rank2) {
+              if (kCta2) tma_load_2d_cta2(dst, tm, fb, cb * kBlockK, h0);
+              else tma_load_2d(dst, tm, fb, cb * kBlockK, h0);
             } else {
-              if (kCta2) tma_load_2d_cta2(dst, &tmB, fb, kb * kBlockK, b_row0);
-              else tma_load_2d(dst, &tmB, fb, kb * kBlockK, b_row0);
+              if (kCta2) tma_load_4d_cta2(dst, tm, fb, cb * kBlockK, dw, h0 + dh, n0);
+              else tma_load_4d(dst, tm, fb, cb * kBlockK, dw, h0 + dh, n0);
             }
+            if (kCta2) tma_load_2d_cta2(dst + kABytes, &tmB, fb, kb * kBlockK, b_row0);
+            else tma_load_2d(dst + kABytes, &tmB, fb, kb * kBlockK, b_row0);
           }
           // advance the k-block state
           ++cb;
@@ -237,7 +229,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           ph = ph_next;
         }
       }
-      if (do_a) TL(5);
+      TL(5);
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (one thread, leader CTA only)
@@ -395,18 +387,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (p.geglu) *reinterpret_cast<float2*>(my_vec + 64 + 2 * lane) = vec_b;
           __syncwarp();
           uint32_t pk[32];
-          uint32_t r2[2][32];
-          if (!p.geglu) {                                   // both halves of the chunk in flight, one wait
-            tmem_ld_x32(t_row + cc * 64, r2[0]);
-            tmem_ld_x32(t_row + cc * 64 + 32, r2[1]);
-            tmem_wait_ld();
-          }
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             const int oc = cc * 64 + hh * 32;              // output column inside the tile
             const int gcol = n_tile * out_cols + oc;       // global output column
-            uint32_t (&r)[32] = r2[hh];
+            uint32_t r[32];
             if (!p.geglu) {
+              tmem_ld_x32(t_row + oc, r);
+              tmem_wait_ld();
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 float v[8];
