@@ -30,13 +30,25 @@
 #include "host_util.h"
 #include "ptx.cuh"
 
+// Build-time variants (A/B-tested on B200; defaults are the faster ones):
+#ifndef B200_EPI_V3
+#define B200_EPI_V3 0            // 1: bias/rowvec via a per-warp smem vector + residual prefetched into registers
+#endif
+#ifndef B200_GEMM_PROFILE
+#define B200_GEMM_PROFILE 0      // 1: CTA-0 cycle timeline + MMA-thread cost breakdown (B200_GEMM_DEBUG & 4 / & 8)
+#endif
+#ifndef B200_SPLIT_PRODUCERS
+#define B200_SPLIT_PRODUCERS 1   // 1: activation (A) and weight (B) TMA streams issued by two different warps
+#endif
+
 namespace b200 {
 
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;              // 64 bf16 = one 128B swizzle row
 static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 static constexpr int kEpiWarps = 8;
-static constexpr int kThreads = 64 + kEpiWarps * 32;    // warp0 TMA, warp1 MMA, warps2-9 epilogue
+static constexpr int kProducerBWarp = 2 + kEpiWarps;    // only with B200_SPLIT_PRODUCERS
+static constexpr int kThreads = 64 + kEpiWarps * 32 + (B200_SPLIT_PRODUCERS ? 32 : 0);   // warp0 TMA, warp1 MMA, warps2-9 epilogue
 static constexpr int kEpiStageBytes = 32 * 128;         // per-warp staging: 32 rows x 64 bf16
 static constexpr int kEpiVecBytes = 128 * 4;            // per-warp bias(+rowvec) vector of the current chunk
 static constexpr int kSmemLimit = 227 * 1024;
@@ -87,10 +99,14 @@ __device__ __forceinline__ float gelu_erf(float g) {
 
 // debug timeline (B200_GEMM_DEBUG & 4): SM cycle counter of CTA 0 at fixed points of the kernel
 __device__ unsigned long long g_timeline[32];
+#if B200_GEMM_PROFILE
 #define TL(i)                                                        \
   do {                                                               \
     if ((p.debug & 4) && blockIdx.x == 0) g_timeline[i] = clock64(); \
   } while (0)
+#else
+#define TL(i) do {} while (0)
+#endif
 
 __device__ __forceinline__ void add8(float (&v)[8], const float* src) {
   const float4 b0 = *reinterpret_cast<const float4*>(src);
@@ -130,7 +146,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmB);
     if (p.tma_out) tma_prefetch_desc(&tmOut);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], B200_SPLIT_PRODUCERS ? 2 : 1);   // one arrive.expect_tx per producer thread
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -159,18 +175,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   pdl_wait();
   if (threadIdx.x == 0) TL(2);
 
-  if (warp == 0) {
-    // ================================================================ TMA producer (one thread)
+  if (warp == 0 || (B200_SPLIT_PRODUCERS && warp == kProducerBWarp)) {
+    // ================================================================ TMA producer (one thread per stream)
     // A single-thread scalar loop, i.e. every instruction costs its full latency: k-block coordinates advance
     // incrementally (no divisions) and the poll of the NEXT stage's empty barrier is issued before the current
     // stage's TMA so that its latency is hidden.  (Splitting A and B over two warps was measured: no gain.)
     if (lane == 0) {
-      const uint32_t my_bytes = static_cast<uint32_t>(stage_bytes) * (kCta2 ? 2u : 1u);   // 2-CTA: leader expects the pair's bytes
+      const bool do_a = !B200_SPLIT_PRODUCERS || warp == 0;
+      const bool do_b = !B200_SPLIT_PRODUCERS || warp != 0;
+      const uint32_t my_bytes = ((do_a ? static_cast<uint32_t>(kABytes) : 0u) + (do_b ? static_cast<uint32_t>(stage_bytes - kABytes) : 0u)) *
+                                (kCta2 ? 2u : 1u);       // 2-CTA: the leader's barrier expects the pair's bytes
       const bool expect = !kCta2 || cta_rank == 0;
       int s = 0;
       uint32_t ph = 0;
-      bool ready = true;                                  // fresh barriers: the first pass over the stages never waits
-      long fills = 0;
+      int fills = 0;
       for (int t = tile0; t < num_tiles; t += tile_step) {
         const int n_tile = t % p.num_n_tiles;
         const int m_group = (t / p.num_n_tiles) % p.num_m_groups;
@@ -189,29 +207,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         int dh = 0, dw = 0;
         if (seg == 0 && p.ntaps == 9) { dh = tap / 3 - 1; dw = tap - (tap / 3) * 3 - 1; }
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          if (!ready) mbar_wait(&empty_bar[s], ph ^ 1);
+          // (a look-ahead test_wait on the next stage was measured: slower -- the producer usually runs ahead, the
+          //  poll fails and the blocking wait still follows)
+          if (fills >= p.stages) mbar_wait(&empty_bar[s], ph ^ 1);       // fresh barriers: the first pass never waits
           uint8_t* dst = smem + s * stage_bytes;
           uint64_t* fb = &full_bar[s];
-          // look ahead: poll the next stage's empty barrier now, use the answer next iteration
           int s_next = s + 1;
           uint32_t ph_next = ph;
           if (s_next == p.stages) { s_next = 0; ph_next ^= 1; }
           ++fills;
-          ready = (fills < p.stages) ? true : mbar_test_wait(&empty_bar[s_next], ph_next ^ 1);
           if ((p.debug & 1) && ph) {                       // timing experiment: operands stay whatever is in smem
             if (cta_rank == 0) mbar_arrive(fb);
           } else {
             if (expect) mbar_expect_tx(fb, my_bytes);
-            const CUtensorMap* tm = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : &tmA2);
-            if (p.a_rank2) {
-              if (kCta2) tma_load_2d_cta2(dst, tm, fb, cb * kBlockK, h0);
-              else tma_load_2d(dst, tm, fb, cb * kBlockK, h0);
-            } else {
-              if (kCta2) tma_load_4d_cta2(dst, tm, fb, cb * kBlockK, dw, h0 + dh, n0);
-              else tma_load_4d(dst, tm, fb, cb * kBlockK, dw, h0 + dh, n0);
+            if (do_a) {
+              // (three literal tensor-map operands: selecting the map through a pointer variable is slower)
+              const int c0 = cb * kBlockK;
+              if (kCta2) {
+                if (seg == 0) tma_load_4d_cta2(dst, &tmA0, fb, c0, dw, h0 + dh, n0);
+                else if (seg == 1) tma_load_4d_cta2(dst, &tmA1, fb, c0, 0, h0, n0);
+                else tma_load_4d_cta2(dst, &tmA2, fb, c0, 0, h0, n0);
+              } else {
+                if (seg == 0) tma_load_4d(dst, &tmA0, fb, c0, dw, h0 + dh, n0);
+                else if (seg == 1) tma_load_4d(dst, &tmA1, fb, c0, 0, h0, n0);
+                else tma_load_4d(dst, &tmA2, fb, c0, 0, h0, n0);
+              }
             }
-            if (kCta2) tma_load_2d_cta2(dst + kABytes, &tmB, fb, kb * kBlockK, b_row0);
-            else tma_load_2d(dst + kABytes, &tmB, fb, kb * kBlockK, b_row0);
+            if (do_b) {
+              if (kCta2) tma_load_2d_cta2(dst + kABytes, &tmB, fb, kb * kBlockK, b_row0);
+              else tma_load_2d(dst + kABytes, &tmB, fb, kb * kBlockK, b_row0);
+            }
           }
           // advance the k-block state
           ++cb;
@@ -229,7 +254,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           ph = ph_next;
         }
       }
-      TL(5);
+      if (do_a) TL(5);
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (one thread, leader CTA only)
@@ -242,8 +267,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       uint64_t a_desc = a_desc0, b_desc = b_desc0;
       int s = 0;
       uint32_t ph = 0;
-      bool ready = false;
-      bool polled = false;
       int it = 0;
       for (int t = tile0; t < num_tiles; t += tile_step, ++it) {
         const int buf = it & 1;
@@ -256,17 +279,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
         if (it == 0) TL(6);
         long long acc_wait = 0, acc_test = 0, acc_fence = 0, acc_mma = 0, acc_rest = 0, n_blocked = 0, tq = 0;
+#if B200_GEMM_PROFILE
         const bool prof = (p.debug & 8) && blockIdx.x == 0;
+#else
+        constexpr bool prof = false;
+#endif
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           if (prof) tq = clock64();
-          if (!(polled && ready)) { mbar_wait(&full_bar[s], ph); ++n_blocked; }
+          mbar_wait(&full_bar[s], ph);
           if (prof) { const long long now = clock64(); acc_wait += now - tq; tq = now; }
-          // look ahead: poll the next stage's full barrier now, use the answer next iteration
           int s_next = s + 1;
           uint32_t ph_next = ph;
           if (s_next == p.stages) { s_next = 0; ph_next ^= 1; }
-          ready = mbar_test_wait(&full_bar[s_next], ph_next);
-          polled = true;
           if (prof) { const long long now = clock64(); acc_test += now - tq; tq = now; }
           tc_fence_after();
           if (prof) { const long long now = clock64(); acc_fence += now - tq; tq = now; }
@@ -346,6 +370,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * p.block_n;
       const int nchunks = p.tma_out ? (out_cols >> 6) : 0;
+#if B200_EPI_V3
       // Per-chunk additive vector (bias + this image's embedding row) goes through a per-warp smem buffer and
       // the residual row segment through registers; both are fetched BEFORE the accumulator is waited for.
       float2 vec_a = make_float2(0.f, 0.f), vec_b = make_float2(0.f, 0.f);
@@ -375,11 +400,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
       };
       if (hf < nchunks) prefetch(hf);
+#endif
       mbar_wait(&tfull_bar[buf], use & 1);
       if (warp == 2 && lane == 0) TL(12);
       tc_fence_after();
 
       if (p.tma_out) {
+#if B200_EPI_V3
         // -------- bf16, stride 1: 64-column chunks -> swizzled smem -> TMA store
         for (int cc = hf; cc < nchunks; cc += 2) {
           __syncwarp();                                     // previous chunk's readers of my_vec are done
@@ -458,6 +485,80 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
           if (warp == 2 && lane == 0) TL(cc == 0 ? 19 : 23);
         }
+#else
+        // -------- bf16, stride 1: 64-column chunks -> swizzled smem -> TMA store
+        for (int cc = hf; cc < nchunks; cc += 2) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int oc = cc * 64 + hh * 32;              // output column inside the tile
+            const int gcol = n_tile * out_cols + oc;       // global output column
+            uint32_t r[32];
+            if (!p.geglu) {
+              tmem_ld_x32(t_row + oc, r);
+              tmem_wait_ld();
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+                const int cg = gcol + g * 8;
+                if (p.bias) add8(v, p.bias + cg);
+                if (row_ok && cg < p.n_valid) {
+                  if (p.rowvec) add8(v, p.rowvec + static_cast<size_t>(n) * p.rowvec_ld + cg);
+                  if (p.residual) {
+                    const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + pix * p.res_ld + cg);
+                    v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                    v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pk[hh * 16 + g * 4 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+              }
+            } else {
+              // GEGLU: tile columns [0, bn/2) are values, [bn/2, bn) the matching gates.
+              uint32_t rg[32];
+              tmem_ld_x32(t_row + oc, r);
+              tmem_ld_x32(t_row + half + oc, rg);
+              tmem_wait_ld();
+              const int bcol = n_tile * p.block_n + oc;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float v[8], gt[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[j] = __uint_as_float(r[g * 8 + j]);
+                  gt[j] = __uint_as_float(rg[g * 8 + j]);
+                }
+                if (p.bias) {
+                  add8(v, p.bias + bcol + g * 8);
+                  add8(gt, p.bias + bcol + half + g * 8);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] *= gelu_erf(gt[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pk[hh * 16 + g * 4 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+              }
+            }
+          }
+          // the previous TMA store of this warp must have finished reading the staging tile
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t addr = stage_row + ((g ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
+                         "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmOut, stage, n_tile * out_cols + cc * 64, q_w, h_t + q_h, n_t + q_n);
+            tma_store_commit();
+          }
+        }
+#endif
       } else {
         // -------- fp32 output and/or stride 2: direct 16-byte stores, 32-column groups
         const int col_base = n_tile * p.block_n;
@@ -655,8 +756,7 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
   CUtensorMap tA[3], tB, tO;
   const void* srcs[3] = {a0, a1 ? a1 : a0, a2 ? a2 : a0};
   const int chans[3] = {c0, c1 ? c1 : c0, c2 ? c2 : c0};
-  static const bool no_rank2 = getenv("B200_GEMM_NO_RANK2") != nullptr;   // debugging knob
-  p.a_rank2 = (ntaps == 1 && w == 1 && nb == 1 && !no_rank2) ? 1 : 0;
+  p.a_rank2 = 0;     // plain 2-D maps for linear layers were measured: no difference to the 4-D box
   for (int i = 0; i < 3; ++i) {
     const uint64_t C = chans[i];
     int rc;

@@ -17,7 +17,7 @@ def main():
     rows = [(x["Kernel Name"], float(x["Metric Value"]), x["Grid Size"]) for x in csv.DictReader(lines)]
     idx = [i for i, (n, _, _) in enumerate(rows) if "sampler_step" in n]
     # the last pair of consecutive sampler launches with only this library's kernels in between
-    mine = ("conv_gemm", "attention_kernel", "groupnorm", "gn_", "layernorm", "time_class_embed", "upsample_nearest", "sampler_step")
+    mine = ("conv_gemm", "attention_kernel", "groupnorm", "gn_", "layernorm", "time_class_embed", "upsample_nearest", "sampler_step", "splitk_reduce")
     step = None
     for a, b in reversed(list(zip(idx[:-1], idx[1:]))):
         cand = rows[a + 1: b + 1]
@@ -37,6 +37,14 @@ def main():
     if not layers:
         return
     L = json.load(open(layers))["rows"]
+    # a split-K layer is one call but two kernels (GEMM + reduce): fold the reduce into the preceding kernel
+    folded = []
+    for n, t, g in step:
+        if "splitk_reduce" in n and folded:
+            folded[-1] = (folded[-1][0], folded[-1][1] + t, folded[-1][2])
+        else:
+            folded.append((n, t, g))
+    step = folded
     if len(L) != len(step):
         print(f"(layers.json has {len(L)} calls, step has {len(step)} kernels: no per-layer table)")
         return
