@@ -87,7 +87,7 @@ def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-PROFILE = None            # set to a list to record (name, start_event, end_event, info) per call
+PROFILE = None            # set to a list to record (name, start_event, end_event, info, args) per call
 
 
 def call(name: str, *args, info=None) -> None:
@@ -99,5 +99,5 @@ def call(name: str, *args, info=None) -> None:
     check(rc, name)
     if PROFILE is not None:
         e1.record()
-        PROFILE.append((name, e0, e1, info))
+        PROFILE.append((name, e0, e1, info, args))
     launch_count += 1

@@ -347,8 +347,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const uint32_t stage_row = smem_u32(stage) + lane * 128;
     const int half = p.block_n / 2;
     const int out_cols = p.geglu ? half : p.block_n;     // output columns per tile
-    float* my_vec = epi_vec + (warp - 2) * (kEpiVecBytes / 4);
-    const bool rv_uniform = p.W * p.BH >= 32;            // the warp's 32 rows lie in one image
+    [[maybe_unused]] float* my_vec = epi_vec + (warp - 2) * (kEpiVecBytes / 4);
+    [[maybe_unused]] const bool rv_uniform = p.W * p.BH >= 32;            // the warp's 32 rows lie in one image
     int it = 0;
     for (int t = tile0; t < num_tiles; t += tile_step, ++it) {
       const int buf = it & 1;
@@ -361,7 +361,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int n_t = (m_tile / p.tiles_h) * p.BNI;
       const int h = h_t + hl;
       const int n = n_t + nl;
-      const int n_warp = n_t + q_n;                        // image of the warp's rows (when rv_uniform)
+      [[maybe_unused]] const int n_warp = n_t + q_n;                        // image of the warp's rows (when rv_uniform)
       bool row_ok = (h < p.H) && (n < p.NB);
       size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + wl;
       if (p.stride == 2) {

@@ -139,8 +139,11 @@ def build_pipeline(device, rank_seed_base: int):
     return pipe
 
 
-def profile_kernels(pipe, lat, pos, neg):
-    """One eager (non-graph) denoising step with CUDA events around every kernel call."""
+def profile_kernels(pipe, lat, pos, neg, reps: int = 8):
+    """Per-kernel device time of one denoising step.  One eager step records every C-ABI call with its arguments;
+    each call is then re-issued `reps` times inside its own CUDA graph and timed with CUDA events on the launching
+    stream (device time per launch without Python / ctypes launch gaps, programmatic dependent launch active as in
+    the real step graph, operands L2-warm)."""
     from audioldm_with_lora_b200 import _lib
     pipe.use_cuda_graph = False
     pipe.denoise(lat, pos, neg, 2, GUIDANCE)            # warm (weights packed, attributes set)
@@ -151,11 +154,27 @@ def profile_kernels(pipe, lat, pos, neg):
     launches = _lib.launch_count - n0
     rec, _lib.PROFILE = _lib.PROFILE, None
     pipe.use_cuda_graph = True
+    lib = _lib.load()
     by = {}
-    for name, e0, e1, info in rec:
+    side = torch.cuda.Stream()
+    for name, _, _, info, cargs in rec:
+        fn = getattr(lib, name)
+        # the recorded stream argument (last) is replaced by the capture stream
+        g = torch.cuda.CUDAGraph()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            a = list(cargs[:-1]) + [side.cuda_stream]
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(reps):
+                    _lib.check(fn(*a), name)
+            g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side); g.replay(); e1.record(side)
+        side.synchronize()
         d = by.setdefault(name, {"ms": 0.0, "calls": 0, "flops": 0.0})
-        d["ms"] += e0.elapsed_time(e1); d["calls"] += 1
+        d["ms"] += e0.elapsed_time(e1) / reps; d["calls"] += 1
         d["flops"] += (info or {}).get("flops", 0.0)
+    torch.cuda.current_stream().wait_stream(side)
     return by, launches
 
 
@@ -285,6 +304,10 @@ def main():
             dist.destroy_process_group()
         return
     sustained, burst, hbm, how = peaks()
+    traffic = None
+    tp = ROOT / "profiles" / "conv_gemm_ncu_traffic.json"        # dram bytes of one profiled launch (ncu --set full)
+    if tp.exists():
+        traffic = json.loads(tp.read_text())
     cg = by.get("b200_conv_gemm", {"ms": 0.0, "calls": 0, "flops": 0.0})
     total_ms = sum(d["ms"] for d in by.values()) or 1.0
     achieved = cg["flops"] / (cg["ms"] / 1e3) / 1e12 if cg["ms"] else 0.0
@@ -305,8 +328,10 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: all conv/linear layers)",
                      "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                      "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
+                     "how": "sum of algorithmic FLOPs of the step's 245 conv/linear launches / sum of their per-launch device "
+                            "times (each launch replayed 8x in its own CUDA graph, CUDA events on the launching stream)",
                      "launches_per_step": cg["calls"], "ms_per_step": cg["ms"], "share_of_step": cg["ms"] / total_ms,
-                     "traffic": None,
+                     "traffic": traffic,
                      "whole_step": {"achieved": unet_flops / (unet_step_ms / 1e3) / 1e12, "frac": unet_flops / (unet_step_ms / 1e3) / 1e12 / sustained}},
         "kernel_breakdown_ms": {k: {"ms": round(v["ms"], 4), "calls": v["calls"],
                                     "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["flops"] and v["ms"] else None}

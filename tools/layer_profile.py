@@ -69,7 +69,7 @@ def main():
         pipe.denoise(lat, pos, neg, 1, 2.5)
         torch.cuda.synchronize()
         rec, _lib.PROFILE = _lib.PROFILE, None
-        runs.append([(n, e0.elapsed_time(e1), info) for n, e0, e1, info in rec])
+        runs.append([(n, e0.elapsed_time(e1), info) for n, e0, e1, info, _ in rec])
     rows = []
     for i, (name, _, info) in enumerate(runs[0]):
         ms = statistics.median(r[i][1] for r in runs)
