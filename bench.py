@@ -219,11 +219,12 @@ def main():
 
     pipe = build_pipeline(device, rank)
     h = int(CLIP_S / 0.01) // 4
-    # prompts are sharded by global index: rank r owns prompts [r*B, (r+1)*B)
+    # prompts are sharded by global index: rank r owns prompts [r*B, (r+1)*B)  (no data-path collective)
+    from audioldm_with_lora_b200.sharding import shard_prompts
     pos_h, neg_h = synthetic.clap_embeddings(BATCH * world)
-    pos_h = pos_h[rank * BATCH:(rank + 1) * BATCH].contiguous().pin_memory()
-    neg_h = neg_h[rank * BATCH:(rank + 1) * BATCH].contiguous().pin_memory()
-    lat_h = synthetic.initial_latents(BATCH, h, first_index=rank * BATCH).pin_memory()
+    pos_h, neg_h, owned = shard_prompts(pos_h, neg_h, rank, world)
+    pos_h, neg_h = pos_h.contiguous().pin_memory(), neg_h.contiguous().pin_memory()
+    lat_h = synthetic.initial_latents(len(owned), h, first_index=owned[0]).pin_memory()
     pos_d, neg_d, lat_d = pos_h.to(device), neg_h.to(device), lat_h.to(device)
 
     def resident_step():
