@@ -4,12 +4,17 @@
 //
 // One CTA = 128 query rows of one (batch, head).  Per 128-key block:
 //   S = Q K^T     tcgen05.mma 128x128x16 (x d/16), operands in smem, S in TMEM
-//   softmax       4 warps, one query row per thread: tcgen05.ld S, online max / exp2 / sum in fp32,
-//                 P (bf16) written to smem in the UMMA K-major core-matrix layout
-//   O_blk = P V   tcgen05.mma 128 x d x 16 (x 8), V consumed straight from the [Q|K|V] GEMM output
-//                 as an MN-major operand (no transposed copy); O_blk in TMEM
-//   acc = acc * alpha + O_blk   in registers (fp32), folded one block late so the PV MMA overlaps
-//                 the next block's max pass.
+//   softmax       4 warps, one query row per thread, ONE pass over S: p = exp2(s*c - m_ref*c) against a lazily
+//                 updated reference maximum m_ref (exact: numerator and denominator share the reference; the
+//                 reference is only moved, and O rescaled, when a row's maximum grows by more than 2^8), two
+//                 probabilities per MUFU op (ex2.approx.ftz.bf16x2 -- P is needed in bf16 anyway), P written to
+//                 smem in the UMMA K-major core-matrix layout
+//   O += P [V|1]  tcgen05.mma 128 x (d+16) x 16 (x 8) accumulating in TMEM across key blocks; V is consumed
+//                 straight from the [Q|K|V] GEMM output as an MN-major operand (no transposed copy), followed in
+//                 smem by 16 columns of ones: O[:, d] is the softmax denominator, summed by the tensor core
+//                 from exactly the bf16 probabilities the numerator uses.
+// With d = 32 the kernel is bound by the softmax instruction stream (exp throughput), not by the tensor pipe:
+// the structure above removes the second pass over S, the per-block O fold and the row-sum adds.
 // Q/K/V tiles are fetched by TMA directly from the fused-QKV activation [B, S, 3C] with a 4-D tensor
 // map (8 elems, rows, 16-byte channel chunks, batch): the box lands as 8x16B core matrices, i.e. the
 // no-swizzle UMMA canonical layout, for any head_dim that is a multiple of 16 (32/48/80 for
@@ -26,22 +31,33 @@ namespace b200 {
 static constexpr int kQ = 128;                 // query rows per CTA
 static constexpr int kKV = 128;                // keys per block
 static constexpr int kAttnThreads = 192;       // warps 0-3 softmax, warp 4 TMA, warp 5 MMA
-static constexpr int kMaxD = 160;
+static constexpr int kOnesBytes = 4096;        // 16 columns of bf16 1.0 behind every V tile (MN-major: 2 chunks x 2048 B)
+static constexpr float kRescaleThreshold = 8.0f;   // move the reference maximum when a row maximum exceeds it by 2^8
 
 struct AttnParams {
   int seq, heads, d, batch;
   int nblk;                 // ceil(seq / 128)
   int stages;               // K/V ring depth (1 or 2)
-  int tmem_cols;            // 256 (d <= 128) or 512
+  int tmem_cols;            // 256 (d + 16 <= 128) or 512
   float scale_log2;         // scale * log2(e)
   __nv_bfloat16* out;
   int out_ld;               // heads * d
-  int variant;              // bit0: swap LBO/SBO of K-major descs, bit1: swap for the MN-major V desc
+  int variant;              // bit0/bit1: descriptor-convention debug knobs; bit2: fp32 exp2 (one MUFU op per element)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t y;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
   return y;
 }
 
@@ -71,11 +87,12 @@ __device__ __forceinline__ float row_max(uint32_t t_row, int kvalid) {
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-// p = exp2(s * scale - m * scale) as bf16 into the K-major core-matrix smem tile; returns the fp32 row sum.
+// One pass over a 128-column S row: p = exp2(s * scale - ref) as bf16 into the K-major core-matrix smem tile.
+// Returns max_j (s_j * scale - ref) (bf16 precision: it only feeds the rescale decision).
 // The next 32-column TMEM load is issued before the current one is processed.
-template <bool kMasked>
-__device__ __forceinline__ float exp_store(uint32_t t_row, uint8_t* sp_row, float scale_log2, float neg_m, int kvalid) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+template <bool kMasked, bool kPackedExp>
+__device__ __forceinline__ float exp_store(uint32_t t_row, uint8_t* sp_row, float scale_log2, float neg_ref, int kvalid) {
+  uint32_t mx = 0xFF80FF80u;                      // (-inf, -inf) in bf16x2
   uint32_t r[2][32];
   tmem_ld_x32(t_row, r[0]);
 #pragma unroll
@@ -85,32 +102,37 @@ __device__ __forceinline__ float exp_store(uint32_t t_row, uint8_t* sp_row, floa
     const uint32_t(&cur)[32] = r[c & 1];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      float e[8];
+      uint32_t pk[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        e[i] = ex2_approx(fmaf(__uint_as_float(cur[g * 8 + i]), scale_log2, neg_m));
-        if (kMasked && c * 32 + g * 8 + i >= kvalid) e[i] = 0.f;
+      for (int i = 0; i < 4; ++i) {
+        const int col = c * 32 + g * 8 + 2 * i;
+        float x0 = fmaf(__uint_as_float(cur[g * 8 + 2 * i]), scale_log2, neg_ref);
+        float x1 = fmaf(__uint_as_float(cur[g * 8 + 2 * i + 1]), scale_log2, neg_ref);
+        if (kMasked) {
+          if (col >= kvalid) x0 = -INFINITY;
+          if (col + 1 >= kvalid) x1 = -INFINITY;
+        }
+        const uint32_t x = pack_bf16x2(x0, x1);
+        mx = max_bf16x2(mx, x);
+        pk[i] = kPackedExp ? ex2_bf16x2(x) : pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
       }
-      s0 += e[0] + e[4]; s1 += e[1] + e[5]; s2 += e[2] + e[6]; s3 += e[3] + e[7];
-      uint4 pk;
-      pk.x = pack_bf16x2(e[0], e[1]); pk.y = pack_bf16x2(e[2], e[3]);
-      pk.z = pack_bf16x2(e[4], e[5]); pk.w = pack_bf16x2(e[6], e[7]);
-      *reinterpret_cast<uint4*>(sp_row + (c * 4 + g) * 2048) = pk;
+      *reinterpret_cast<uint4*>(sp_row + (c * 4 + g) * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
-  return (s0 + s1) + (s2 + s3);
+  return fmaxf(bf16_lo(mx), bf16_hi(mx));
 }
 
-template <int D>
-__device__ __forceinline__ void fold_o(uint32_t t_o, float (&acc)[kMaxD], float alpha) {
-#pragma unroll
-  for (int c = 0; c < D / 16; ++c) {
+// O (TMEM, ncols fp32 columns of this thread's row) *= f
+__device__ __forceinline__ void scale_o(uint32_t t_o_row, int ncols, float f) {
+  for (int c = 0; c < ncols / 16; ++c) {
     uint32_t r[16];
-    tmem_ld_x16(t_o + c * 16, r);
+    tmem_ld_x16(t_o_row + c * 16, r);
     tmem_wait_ld();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[c * 16 + j] = acc[c * 16 + j] * alpha + __uint_as_float(r[j]);
+    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * f);
+    tmem_st_x16(t_o_row + c * 16, r);
   }
+  tmem_wait_st();
 }
 
 template <int D>
@@ -120,10 +142,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   constexpr int kTileBytes = 128 * D * 2;       // one Q / K / V tile
   constexpr int kPBytes = kQ * kKV * 2;
+  constexpr int kStageBytes = 2 * kTileBytes + kOnesBytes;      // K tile, V tile, ones columns
+  constexpr int kOCols = D + 16;                // O accumulator columns: d outputs + the denominator (x16)
   uint8_t* sQ = smem;
   uint8_t* sP = sQ + kTileBytes;
-  uint8_t* sKV = sP + kPBytes;                  // stages x {K, V}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + p.stages * 2 * kTileBytes);
+  uint8_t* sKV = sP + kPBytes;                  // stages x {K, V, ones}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + p.stages * kStageBytes);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                 // [2]
   uint64_t* kv_empty = bars + 3;                // [2]
@@ -155,6 +179,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
+  // the ones columns behind every V tile (never overwritten: the TMA box covers the V tile only)
+  for (int i = threadIdx.x; i < p.stages * (kOnesBytes / 16); i += kAttnThreads) {
+    const int st = i / (kOnesBytes / 16), off = i % (kOnesBytes / 16);
+    *reinterpret_cast<uint4*>(sKV + st * kStageBytes + 2 * kTileBytes + off * 16) =
+        make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  }
+  fence_proxy_async_smem();
   if (warp == 4) {
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
@@ -166,7 +197,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
   pdl_launch_dependents();
   pdl_wait();
   const uint32_t t_s = tmem_base;               // S: columns [0, 128)
-  const uint32_t t_o = tmem_base + 128;         // O_blk: columns [128, 128 + D)
+  const uint32_t t_o = tmem_base + 128;         // O: columns [128, 128 + D + 16)
 
   if (warp == 4) {
     // ============================================================ TMA producer
@@ -177,7 +208,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
       uint32_t ph = 0;
       for (int j = 0; j < p.nblk; ++j) {
         mbar_wait(&kv_empty[s], ph ^ 1);
-        uint8_t* k_dst = sKV + s * 2 * kTileBytes;
+        uint8_t* k_dst = sKV + s * kStageBytes;
         mbar_expect_tx(&kv_full[s], 2 * kTileBytes);
         tma_load_4d(k_dst, &tmQKV, &kv_full[s], 0, j * kKV, chunk_k, b);
         tma_load_4d(k_dst + kTileBytes, &tmQKV, &kv_full[s], 0, j * kKV, chunk_v, b);
@@ -191,7 +222,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
     // ============================================================ MMA issuer
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-      const uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);       // B = V, MN-major
+      const uint32_t idesc_o = make_idesc_bf16(128, kOCols, 0, 1);  // B = [V | 1], MN-major
       // no-swizzle canonical layouts: core matrix = 8 rows x 16 B, contiguous (128 B).
       //  K-major tile [128 rows][D]: next 8-row group +128 B (SBO), next 8-elem K chunk +2048 B (LBO)
       //  MN-major V   [128 keys][D]: next 8-key group +128 B (LBO), next 8-elem d chunk +2048 B (SBO)
@@ -203,7 +234,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < p.nblk; ++j) {
-        const uint32_t k_addr = smem_u32(sKV + s * 2 * kTileBytes);
+        const uint32_t k_addr = smem_u32(sKV + s * kStageBytes);
         const uint32_t v_addr = k_addr + kTileBytes;
         mbar_wait(&kv_full[s], ph);
         tc_fence_after();
@@ -215,14 +246,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
           umma_bf16_ss(t_s, a_desc, b_desc, idesc_s, k != 0);
         }
         umma_commit(s_full);
-        // O_blk = P V
+        // O += P [V | 1]   (the softmax threads rescaled O, if needed, before they released p_full)
         mbar_wait(p_full, j & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < kKV / 16; ++k) {
           const uint64_t a_desc = make_smem_desc(p_addr + k * 4096, k_lbo, k_sbo, SWZ_NONE);
           const uint64_t b_desc = make_smem_desc(v_addr + k * 256, v_lbo, v_sbo, SWZ_NONE);
-          umma_bf16_ss(t_o, a_desc, b_desc, idesc_o, k != 0);
+          umma_bf16_ss(t_o, a_desc, b_desc, idesc_o, (j | k) != 0);
         }
         umma_commit(o_full);
         umma_commit(&kv_empty[s]);
@@ -233,54 +264,71 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
       }
     }
   } else {
-    // ============================================================ softmax + accumulate (row = thread)
+    // ============================================================ softmax (row = thread)
     const int row = warp * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    float acc[kMaxD];
-#pragma unroll
-    for (int i = 0; i < D; ++i) acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+    const bool packed = (p.variant & 4) == 0;
+    uint8_t* sp_row = sP + row * 16;
+    float ref = 0.f;                              // reference maximum, in exponent units: m_ref * scale * log2(e)
     for (int j = 0; j < p.nblk; ++j) {
       const int kvalid = min(kKV, p.seq - j * kKV);
+      const bool full = kvalid == kKV;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max (keys past the end of the sequence only exist in the last block)
-      const float mx = (kvalid == kKV) ? row_max<false>(t_s + lane_off, kvalid) : row_max<true>(t_s + lane_off, kvalid);
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);
-      const float neg_m = -m_new * p.scale_log2;
-      // fold the previous block's P V (also guarantees sP is free again)
-      if (j > 0) {
+      if (j == 0) {
+        const float mx = full ? row_max<false>(t_s + lane_off, kvalid) : row_max<true>(t_s + lane_off, kvalid);
+        ref = mx * p.scale_log2;
+      } else {
+        // sP is free again (and O is quiescent) once the previous block's P V has completed
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
-        fold_o<D>(t_o + lane_off, acc, alpha_prev);
       }
-      // pass 2: p = exp2(s * c - m * c) -> bf16 -> smem (K-major core matrices), row sum
-      const float sum = (kvalid == kKV) ? exp_store<false>(t_s + lane_off, sP + row * 16, p.scale_log2, neg_m, kvalid)
-                                        : exp_store<true>(t_s + lane_off, sP + row * 16, p.scale_log2, neg_m, kvalid);
-      l_run = l_run * alpha + sum;
-      m_run = m_new;
-      alpha_prev = alpha;
+      float over;
+      if (packed) over = full ? exp_store<false, true>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
+                              : exp_store<true, true>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid);
+      else over = full ? exp_store<false, false>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
+                       : exp_store<true, false>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid);
+      // warp-uniform decision (the TMEM loads / stores below are warp-collective)
+      if (__any_sync(0xffffffffu, over > kRescaleThreshold)) {
+        // rare: a row's maximum moved by more than 2^8 -> every row of the warp takes its current maximum as the
+        // new reference, O (with its denominator column) is rescaled, and the block's probabilities are redone
+        const float mx = full ? row_max<false>(t_s + lane_off, kvalid) : row_max<true>(t_s + lane_off, kvalid);
+        const float new_ref = fmaxf(ref, mx * p.scale_log2);
+        scale_o(t_o + lane_off, kOCols, ex2_approx(ref - new_ref));
+        ref = new_ref;
+        if (packed) (void)(full ? exp_store<false, true>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
+                                : exp_store<true, true>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid));
+        else (void)(full ? exp_store<false, false>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
+                         : exp_store<true, false>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid));
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }
     mbar_wait(o_full, (p.nblk - 1) & 1);
     tc_fence_after();
-    // last block: its own alpha was already applied to l_run; acc still needs alpha_last
-    fold_o<D>(t_o + lane_off, acc, alpha_prev);
+    // epilogue: O[:, :d] / O[:, d]
     const int qrow = q0 + row;
-    if (qrow < p.seq) {
-      const float inv = 1.0f / l_run;
-      __nv_bfloat16* o = p.out + (static_cast<size_t>(b) * p.seq + qrow) * p.out_ld + h * D;
+    uint32_t rl[16];
+    tmem_ld_x16(t_o + lane_off + D, rl);
+    tmem_wait_ld();
+    const float inv = 1.0f / __uint_as_float(rl[0]);
+    __nv_bfloat16* o = p.out + (static_cast<size_t>(b) * p.seq + qrow) * p.out_ld + h * D;
 #pragma unroll
-      for (int g = 0; g < D / 8; ++g) {
-        uint4 pk;
-        pk.x = pack_bf16x2(acc[g * 8 + 0] * inv, acc[g * 8 + 1] * inv);
-        pk.y = pack_bf16x2(acc[g * 8 + 2] * inv, acc[g * 8 + 3] * inv);
-        pk.z = pack_bf16x2(acc[g * 8 + 4] * inv, acc[g * 8 + 5] * inv);
-        pk.w = pack_bf16x2(acc[g * 8 + 6] * inv, acc[g * 8 + 7] * inv);
-        *reinterpret_cast<uint4*>(o + g * 8) = pk;
+    for (int c = 0; c < D / 16; ++c) {
+      uint32_t r[16];
+      tmem_ld_x16(t_o + lane_off + c * 16, r);
+      tmem_wait_ld();
+      if (qrow < p.seq) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * inv, __uint_as_float(r[g * 8 + 1]) * inv);
+          pk.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv, __uint_as_float(r[g * 8 + 3]) * inv);
+          pk.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv, __uint_as_float(r[g * 8 + 5]) * inv);
+          pk.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv, __uint_as_float(r[g * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(o + c * 16 + g * 8) = pk;
+        }
       }
     }
     tc_fence_before();
@@ -296,11 +344,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
 template <int D>
 static int launch_attention(const CUtensorMap& tm, AttnParams& p, cudaStream_t stream) {
   constexpr int kTileBytes = 128 * D * 2;
+  constexpr int kStageBytes = 2 * kTileBytes + kOnesBytes;
   const int fixed = kTileBytes + kQ * kKV * 2 + 128 /*barriers*/ + 128 /*align*/;
   // two resident CTAs per SM when TMEM allows (256 columns each)
   const int budget = (p.tmem_cols <= 256) ? 110 * 1024 : 220 * 1024;
-  p.stages = (fixed + 2 * 2 * kTileBytes <= budget) ? 2 : 1;
-  const int smem_bytes = fixed + p.stages * 2 * kTileBytes;
+  p.stages = (fixed + 2 * kStageBytes <= budget) ? 2 : 1;
+  const int smem_bytes = fixed + p.stages * kStageBytes;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -326,7 +375,7 @@ extern "C" int b200_attention(const void* qkv, void* out, int batch, int seq, in
   memset(&p, 0, sizeof(p));
   p.seq = seq; p.heads = heads; p.d = head_dim; p.batch = batch;
   p.nblk = (seq + kKV - 1) / kKV;
-  p.tmem_cols = (head_dim <= 128) ? 256 : 512;
+  p.tmem_cols = (head_dim + 16 <= 128) ? 256 : 512;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.out_ld = C;
