@@ -17,6 +17,7 @@ Data layout in HBM
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -97,6 +98,9 @@ class UNetEngine:
         self.attn_variant = 0
         self.weights_version = 0      # bumped whenever packed device weights are (re)built
         self.arena: Optional[Arena] = None
+        # concurrent sub-batch branches (forward_branched): per-branch arenas and side streams
+        self._branch_arenas: Dict[int, List[Arena]] = {}
+        self._branch_streams: List["torch.cuda.Stream"] = []
         self._init_small()
 
     # ------------------------------------------------------------------ weights
@@ -250,12 +254,38 @@ class UNetEngine:
                     W[p + ".to_out"] = self._pw([wo], bo, mt, 1, c)
 
     # ------------------------------------------------------------------ arena
-    def _ensure_arena(self, nb: int, h: int, w: int) -> Arena:
+    def _arena_bytes(self, nb: int, h: int, w: int) -> int:
         c0 = self.cfg.block_out_channels[0]
-        need = nb * h * w * c0 * 2 * 40 + (64 << 20)      # ~40 level-0-sized bf16 tensors: generous
+        return nb * h * w * c0 * 2 * 40 + (64 << 20)      # ~40 level-0-sized bf16 tensors: generous
+
+    def _ensure_arena(self, nb: int, h: int, w: int) -> Arena:
+        need = self._arena_bytes(nb, h, w)
         if self.arena is None or self.arena.buf.numel() < need:
             self.arena = Arena(need, self.device)
         return self.arena
+
+    def _ensure_branches(self, branches: int, nb_sub: int, h: int, w: int) -> List[Arena]:
+        need = self._arena_bytes(nb_sub, h, w)
+        ars = self._branch_arenas.get(branches)
+        if ars is None or ars[0].buf.numel() < need:
+            ars = self._branch_arenas[branches] = [Arena(need, self.device) for _ in range(branches)]
+        while self.device.type == "cuda" and len(self._branch_streams) < branches - 1:
+            self._branch_streams.append(torch.cuda.Stream(device=self.device))
+        return ars
+
+    def arena_token(self, nb: int, h: int, w: int, branches: int = 1) -> tuple:
+        """Identity of the device buffers a captured CUDA graph of this shape points into."""
+        branches = self.effective_branches(nb, branches)
+        if branches > 1:
+            return tuple(id(a) for a in self._ensure_branches(branches, nb // branches, h, w))
+        return (id(self._ensure_arena(nb, h, w)),)
+
+    @staticmethod
+    def effective_branches(nb: int, branches: int) -> int:
+        branches = max(1, int(branches))
+        while branches > 1 and nb % branches:
+            branches -= 1
+        return branches
 
     # ------------------------------------------------------------------ forward
     def embed(self, t_steps: Tensor, step_ptr: Optional[Tensor], per_sample: bool, labels: Tensor,
@@ -267,21 +297,55 @@ class UNetEngine:
                              S["time_embedding.linear_2.bias"], S["class_embedding.weight"], S["class_embedding.bias"],
                              emb_out, silu_out)
 
+    def forward_branched(self, xin: Tensor, silu_emb: Tensor, nb: int, h: int, w: int, eps_out: Tensor,
+                         branches: int = 2, attn_overrides: Optional[dict] = None) -> Tensor:
+        """The UNet is one long dependency chain of mostly sub-wave kernels (at the 63x4 / 32x2 levels a layer has
+        8..32 tiles for 148 SMs), and every sample of the batch is independent: split the batch into `branches`
+        sub-batches, each with its own arena on its own stream and a 148/branches-CTA cap for the persistent GEMM
+        kernels, so that the chains overlap each other's launch latencies, prologues and tails.  Captured into the
+        denoising-step CUDA graph as parallel branches (fork after the embedding kernel, join before the sampler)."""
+        branches = self.effective_branches(nb, branches)
+        if branches <= 1 or attn_overrides:
+            return self.forward_nhwc(xin, silu_emb, nb, h, w, eps_out, attn_overrides=attn_overrides)
+        sub = nb // branches
+        arenas = self._ensure_branches(branches, sub, h, w)
+        cap = int(os.environ.get("B200_BRANCH_CAP", "0")) or max(1, ops.NUM_SMS // branches)
+
+        def run(b):
+            self.forward_nhwc(xin[b * sub:(b + 1) * sub], silu_emb[b * sub:(b + 1) * sub], sub, h, w,
+                              eps_out[b * sub:(b + 1) * sub], arena=arenas[b], max_ctas=cap)
+
+        if self.device.type != "cuda":          # host-logic tests (tests/fake_ops.py): same split, no streams
+            for b in range(branches):
+                run(b)
+            return eps_out
+        cur = torch.cuda.current_stream()
+        streams = [cur] + self._branch_streams[: branches - 1]
+        for s in streams[1:]:
+            s.wait_stream(cur)                  # fork point: BEFORE anything of branch 0 is enqueued on `cur`
+        for b, s in enumerate(streams):
+            with torch.cuda.stream(s):
+                run(b)
+        for s in streams[1:]:
+            cur.wait_stream(s)
+        return eps_out
+
     def forward_nhwc(self, xin: Tensor, silu_emb: Tensor, nb: int, h: int, w: int, eps_out: Tensor,
-                     taps: Optional[dict] = None, attn_overrides: Optional[dict] = None) -> Tensor:
+                     taps: Optional[dict] = None, attn_overrides: Optional[dict] = None,
+                     arena: Optional[Arena] = None, max_ctas: int = 0) -> Tensor:
         """xin bf16 [nb, h, w, 64] (channels >= 8 zero), silu_emb bf16 [nb, temb_channels]
         -> eps_out fp32 [nb, h*w, 8] (NHWC)."""
         cfg, g = self.cfg, self.graph
         plan = self._plan(nb, h, w)
         W, sizes, S = plan["W"], plan["sizes"], self._small
-        ar = self._ensure_arena(nb, h, w)
+        ar = arena if arena is not None else self._ensure_arena(nb, h, w)
         bf16 = torch.bfloat16
 
         def M(lvl):
             return nb * sizes[lvl][0] * sizes[lvl][1]
 
         rowvec = ar.alloc((nb, plan["temb_total"]), torch.float32)
-        ops.conv_gemm(W["temb"], silu_emb, 1, nb, 1, rowvec, out_ld=plan["temb_total"])
+        ops.conv_gemm(W["temb"], silu_emb, 1, nb, 1, rowvec, out_ld=plan["temb_total"], max_ctas=max_ctas)
 
         def tap(name, buf, lvl, c):
             if taps is not None:
@@ -308,7 +372,7 @@ class UNetEngine:
             rv = rowvec[:, rowvec_off:] if rowvec_off is not None else None
             ws = splitk_ws(pw, lvl, stride, out.dtype == torch.float32)
             ops.conv_gemm(pw, a0, nb, hh, ww, out, a1=a1, a2=a2, stride=stride, rowvec=rv,
-                          rowvec_ld=plan["temb_total"], residual=residual, workspace=ws)
+                          rowvec_ld=plan["temb_total"], residual=residual, workspace=ws, max_ctas=max_ctas)
             ar.release(ws)
             return out
 
@@ -316,7 +380,7 @@ class UNetEngine:
             pw = W[name]
             out = ar.alloc((M(lvl), pw.n_valid), bf16)
             ws = splitk_ws(pw, lvl)
-            ops.conv_gemm(pw, a0, 1, M(lvl), 1, out, a1=a1, residual=residual, workspace=ws)
+            ops.conv_gemm(pw, a0, 1, M(lvl), 1, out, a1=a1, residual=residual, workspace=ws, max_ctas=max_ctas)
             ar.release(ws)
             return out
 

@@ -12,6 +12,7 @@ host synchronisation.  VAE decode and the HiFi-GAN vocoder stay torch-eager (BAS
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Tuple, Union
 
@@ -56,16 +57,18 @@ class _LoopState:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_key = None
 
-    def one_step(self, eng, guidance: float, overrides=None) -> None:
+    def one_step(self, eng, guidance: float, overrides=None, branches: int = 1) -> None:
         eng.embed(self.t_steps, self.step, False, self.labels, None, self.silu_emb)
-        eng.forward_nhwc(self.xin, self.silu_emb, self.nb_unet, self.h, self.w, self.eps, attn_overrides=overrides)
+        eng.forward_branched(self.xin, self.silu_emb, self.nb_unet, self.h, self.w, self.eps, branches=branches,
+                             attn_overrides=overrides)
         ops.sampler_step(self.eps, self.x, self.x_saved, self.hist, self.table, self.step, guidance, self.do_cfg,
                          self.nb_lat, self.h * self.w, eng.cfg.in_channels, LATENT_C_PAD, self.xin)
 
 
 class AudioLDMPipeline:
     def __init__(self, unet: UNet2DConditionModel, scheduler: Optional[DDIMScheduler] = None, vae=None, vocoder=None,
-                 text_encoder=None, tokenizer=None, tail_dtype: torch.dtype = torch.bfloat16, use_cuda_graph: bool = True):
+                 text_encoder=None, tokenizer=None, tail_dtype: torch.dtype = torch.bfloat16, use_cuda_graph: bool = True,
+                 branches: Optional[int] = None):
         self.unet = unet
         self.scheduler = scheduler or DDIMScheduler()
         self.vae, self.vocoder = vae, vocoder
@@ -73,6 +76,10 @@ class AudioLDMPipeline:
         self.device = unet.b200_device
         self.tail_dtype = tail_dtype
         self.use_cuda_graph = use_cuda_graph
+        # concurrent sub-batch chains inside one denoising step (engine.forward_branched).  Measured on B200 at the
+        # bench workload (UNet batch 16): 1 chain 5.53 ms/step, 2 chains 6.19, 4 chains 7.6 -- the step is bound by
+        # per-tile latency on already-occupied SMs, not by idle SMs, so one chain is the default.
+        self.branches = int(os.environ.get("B200_BRANCHES", "1")) if branches is None else int(branches)
         self._loops: Dict[tuple, _LoopState] = {}
         if self.vae is not None:
             self.vae = self.vae.to(self.device, tail_dtype).eval()
@@ -193,23 +200,24 @@ class AudioLDMPipeline:
             st.labels.copy_(prompt_embeds)
         guidance = float(guidance_scale)
         overrides = self.unet.custom_attn_processors()
-        eng._plan(st.nb_unet, h, w)          # make sure weights are packed before the graph key is taken
-        eng._ensure_arena(st.nb_unet, h, w)
-        graph_key = (guidance, eng.weights_version, id(eng.arena), tuple(sorted(overrides or ())))
+        branches = 1 if overrides else eng.effective_branches(st.nb_unet, self.branches)
+        eng._plan(st.nb_unet // branches, h, w)          # make sure weights are packed before the graph key is taken
+        graph_key = (guidance, eng.weights_version, eng.arena_token(st.nb_unet, h, w, branches), branches,
+                     tuple(sorted(overrides or ())))
         if self.use_cuda_graph and (st.graph is None or st.graph_key != graph_key):
             # warm-up on a side stream (packs weights, sets func attributes), then capture one step
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 saved = (st.x.clone(), st.xin.clone())
-                st.one_step(eng, guidance, overrides)
+                st.one_step(eng, guidance, overrides, branches)
                 st.step.zero_(); st.x.copy_(saved[0]); st.xin.copy_(saved[1])
                 if st.hist is not None:
                     st.hist.zero_()
             torch.cuda.current_stream().wait_stream(s)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                st.one_step(eng, guidance, overrides)
+                st.one_step(eng, guidance, overrides, branches)
             st.graph, st.graph_key = g, graph_key
             st.launches_per_step = None
         need_host = callback is not None or trace is not None
@@ -217,7 +225,7 @@ class AudioLDMPipeline:
             if self.use_cuda_graph:
                 st.graph.replay()
             else:
-                st.one_step(eng, guidance, overrides)
+                st.one_step(eng, guidance, overrides, branches)
             if need_host:
                 cur = st.x.view(nb, h, w, c).permute(0, 3, 1, 2).contiguous()
                 if trace is not None:
