@@ -47,6 +47,23 @@ _PROTOS = {
     "b200_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_float,
                                 c_float, c_int, c_float, c_void_p]),
     "b200_mse_partial": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_void_p]),
+    # ---- fine-tuning step (forward variants that keep what the backward needs, and the backward kernels)
+    "b200_attention_lse": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "b200_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_float, c_void_p]),
+    "b200_groupnorm_silu_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                          c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200_groupnorm_silu_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                        c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
+    "b200_geglu_fwd": (c_int, [c_void_p, c_long, c_int, c_void_p, c_void_p]),
+    "b200_geglu_bwd": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p, c_void_p]),
+    "b200_lora_wgrad": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "b200_zero_insert": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_upsample_nearest_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_add_bf16": (c_int, [c_void_p, c_void_p, c_long, c_void_p]),
+    "b200_mse_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "b200_lora_refresh": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
 }
 EXPORTS = tuple(_PROTOS)
 

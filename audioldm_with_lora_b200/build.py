@@ -13,7 +13,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libb200ldm.so"
-SOURCES = ["conv_gemm.cu", "attention.cu", "norm.cu", "sampler.cu", "train.cu"]
+SOURCES = ["conv_gemm.cu", "attention.cu", "attention_bwd.cu", "norm.cu", "sampler.cu", "train.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

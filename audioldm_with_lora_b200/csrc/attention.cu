@@ -43,6 +43,7 @@ struct AttnParams {
   __nv_bfloat16* out;
   int out_ld;               // heads * d
   int variant;              // bit0/bit1: descriptor-convention debug knobs; bit2: fp32 exp2 (one MUFU op per element)
+  float* lse;               // optional [batch, heads, seq] fp32: log2-domain log-sum-exp of the scaled scores (training)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -313,6 +314,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
     tmem_ld_x16(t_o + lane_off + D, rl);
     tmem_wait_ld();
     const float inv = 1.0f / __uint_as_float(rl[0]);
+    if (p.lse != nullptr && qrow < p.seq)      // p_ij = exp2(s_ij * scale_log2 - lse): what the backward kernel recomputes
+      p.lse[(static_cast<size_t>(b) * p.heads + h) * p.seq + qrow] = ref + log2f(__uint_as_float(rl[0]));
     __nv_bfloat16* o = p.out + (static_cast<size_t>(b) * p.seq + qrow) * p.out_ld + h * D;
 #pragma unroll
     for (int c = 0; c < D / 16; ++c) {
@@ -365,8 +368,22 @@ static int launch_attention(const CUtensorMap& tm, AttnParams& p, cudaStream_t s
 
 using namespace b200;
 
+static int attention_impl(const void* qkv, void* out, float* lse, int batch, int seq, int heads, int head_dim, float scale,
+                          int variant, void* stream_v);
+
 extern "C" int b200_attention(const void* qkv, void* out, int batch, int seq, int heads, int head_dim, float scale,
                               int variant, void* stream_v) {
+  return attention_impl(qkv, out, nullptr, batch, seq, heads, head_dim, scale, variant, stream_v);
+}
+// Training form: also writes the per-row log-sum-exp (log2 domain, scale folded in) the backward kernel needs.
+extern "C" int b200_attention_lse(const void* qkv, void* out, float* lse, int batch, int seq, int heads, int head_dim,
+                                  float scale, void* stream_v) {
+  B200_CHECK_ARG(lse, "attention_lse: null lse");
+  return attention_impl(qkv, out, lse, batch, seq, heads, head_dim, scale, 0, stream_v);
+}
+
+static int attention_impl(const void* qkv, void* out, float* lse, int batch, int seq, int heads, int head_dim, float scale,
+                          int variant, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   B200_CHECK_ARG(qkv && out, "attention: null pointer");
   B200_CHECK_ARG(batch > 0 && seq > 0 && heads > 0, "attention: empty problem");
@@ -380,6 +397,7 @@ extern "C" int b200_attention(const void* qkv, void* out, int batch, int seq, in
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.out_ld = C;
   p.variant = variant;
+  p.lse = lse;
 
   CUtensorMap tm;
   {

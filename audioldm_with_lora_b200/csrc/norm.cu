@@ -38,6 +38,7 @@ struct GnParams {
   float eps;
   int silu;
   __nv_bfloat16* y;
+  float* stats;             // optional [nb, groups, 2] = (mean, rstd): kept for the backward pass (training)
 };
 
 // grid (cluster_size, NB, gsplit), cluster (cluster_size, 1, 1): blockIdx.x = rank of the CTA in its cluster
@@ -141,6 +142,11 @@ groupnorm_silu_kernel(const GnParams p) {
     const float var = fmaxf(s_gpart[64 + 2 * tid + 1] / cnt - mean * mean, 0.f);
     s_mean[tid] = mean;
     s_rstd[tid] = rsqrtf(var + p.eps);
+    if (p.stats != nullptr && rank == 0) {
+      float* st = p.stats + (static_cast<size_t>(n) * p.groups + blockIdx.z * gl + tid) * 2;
+      st[0] = mean;
+      st[1] = s_rstd[tid];
+    }
   }
   __syncthreads();
 
@@ -252,9 +258,24 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int M, int C, const float*
 
 using namespace b200;
 
+static int groupnorm_impl(const void* x0, int c0, const void* x1, int c1, int nb, int hw, int groups, const float* gamma,
+                          const float* beta, float eps, int silu, void* y, float* stats, void* stream_v);
+
 extern "C" int b200_groupnorm_silu(const void* x0, int c0, const void* x1, int c1, int nb, int hw, int groups,
                                    const float* gamma, const float* beta, float eps, int silu, void* y,
                                    void* stream_v) {
+  return groupnorm_impl(x0, c0, x1, c1, nb, hw, groups, gamma, beta, eps, silu, y, nullptr, stream_v);
+}
+// Training form: also writes (mean, rstd) per (image, group) for b200_groupnorm_silu_bwd.
+extern "C" int b200_groupnorm_silu_stats(const void* x0, int c0, const void* x1, int c1, int nb, int hw, int groups,
+                                         const float* gamma, const float* beta, float eps, int silu, void* y,
+                                         float* stats, void* stream_v) {
+  B200_CHECK_ARG(stats, "groupnorm_stats: null stats");
+  return groupnorm_impl(x0, c0, x1, c1, nb, hw, groups, gamma, beta, eps, silu, y, stats, stream_v);
+}
+
+static int groupnorm_impl(const void* x0, int c0, const void* x1, int c1, int nb, int hw, int groups, const float* gamma,
+                          const float* beta, float eps, int silu, void* y, float* stats, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const int C = c0 + c1;
   B200_CHECK_ARG(x0 && y && gamma && beta, "groupnorm: null pointer");
@@ -266,6 +287,7 @@ extern "C" int b200_groupnorm_silu(const void* x0, int c0, const void* x1, int c
   p.x0 = reinterpret_cast<const __nv_bfloat16*>(x0); p.x1 = reinterpret_cast<const __nv_bfloat16*>(x1);
   p.C0 = c0; p.C1 = c1; p.HW = hw; p.groups = groups; p.gamma = gamma; p.beta = beta; p.eps = eps; p.silu = silu;
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.stats = stats;
   // Launch shape: cluster size cs (pixel slabs of one image) x gsplit (independent halves / quarters of the
   // groups), the combination with the most CTAs whose clusters are all co-resident (one wave).
   static int max_active[4] = {-1, -1, -1, -1};      // for cs = 1, 2, 4, 8

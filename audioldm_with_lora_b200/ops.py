@@ -5,10 +5,11 @@ stream; tensors are borrowed, outputs are caller-allocated.
 """
 from __future__ import annotations
 
+import ctypes
 import math
 import os
 from dataclasses import dataclass
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 
@@ -227,3 +228,113 @@ def adamw_flat(param: Tensor, grad: Tensor, m: Tensor, v: Tensor, lr: float, bet
 
 def mse_partial(pred: Tensor, target: Tensor, out_sum: Tensor) -> None:
     call("b200_mse_partial", ptr(pred), ptr(target), pred.numel(), ptr(out_sum), stream())
+
+
+# ------------------------------------------------------------------------------------------ fine-tuning step
+class WgradDesc(ctypes.Structure):
+    """One (U, V) pair of b200_lora_wgrad: G[c, j] += scale * sum_m U[m, c] V[m, j] -> out[c*ldc + j*ldj] (fp32)."""
+    _fields_ = [("u", ctypes.c_void_p), ("v", ctypes.c_void_p), ("out", ctypes.c_void_p), ("ldu", ctypes.c_int),
+                ("ldv", ctypes.c_int), ("C", ctypes.c_int), ("r", ctypes.c_int), ("ldc", ctypes.c_int),
+                ("ldj", ctypes.c_int), ("scale", ctypes.c_float)]
+
+
+REFRESH_DTYPE = [("dst", "<u8"), ("src_off", "<i8"), ("dst_ld", "<i4"), ("src_rows", "<i4"), ("src_cols", "<i4"),
+                 ("transpose", "<i4"), ("scale", "<f4"), ("pad", "<i4")]      # struct RefreshDesc in csrc/train.cu
+
+
+def attention_lse(qkv: Tensor, out: Tensor, lse: Tensor, batch: int, seq: int, heads: int, head_dim: int,
+                  scale: Optional[float] = None) -> Tensor:
+    assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and lse.dtype == torch.float32
+    assert lse.numel() == batch * heads * seq
+    if scale is None:
+        scale = head_dim ** -0.5
+    info = ({"flops": 4.0 * batch * heads * seq * seq * head_dim, "desc": f"b{batch} s{seq} d{head_dim}"}
+            if _lib.PROFILE is not None else None)
+    call("b200_attention_lse", ptr(qkv), ptr(out), ptr(lse), batch, seq, heads, head_dim, float(scale), stream(), info=info)
+    return out
+
+
+def attention_bwd(qkv: Tensor, o: Tensor, dout: Tensor, lse: Tensor, delta: Tensor, dqkv: Tensor, batch: int, seq: int,
+                  heads: int, head_dim: int, scale: Optional[float] = None) -> Tensor:
+    for t in (qkv, o, dout, dqkv):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous()
+    assert lse.dtype == torch.float32 and delta.dtype == torch.float32 and delta.numel() == lse.numel()
+    if scale is None:
+        scale = head_dim ** -0.5
+    info = ({"flops": 14.0 * batch * heads * seq * seq * head_dim, "desc": f"b{batch} s{seq} d{head_dim}"}
+            if _lib.PROFILE is not None else None)
+    call("b200_attention_bwd", ptr(qkv), ptr(o), ptr(dout), ptr(lse), ptr(delta), ptr(dqkv), batch, seq, heads, head_dim,
+         float(scale), stream(), info=info)
+    return dqkv
+
+
+def groupnorm_silu_stats(x0: Tensor, c0: int, x1: Optional[Tensor], c1: int, nb: int, hw: int, gamma: Tensor,
+                         beta: Tensor, eps: float, silu: bool, y: Tensor, stats: Tensor, groups: int = 32) -> Tensor:
+    assert x0.dtype == torch.bfloat16 and y.dtype == torch.bfloat16 and stats.dtype == torch.float32
+    assert stats.numel() == nb * groups * 2
+    call("b200_groupnorm_silu_stats", ptr(x0), c0, ptr(x1) if c1 else None, c1, nb, hw, groups, ptr(gamma), ptr(beta),
+         float(eps), int(silu), ptr(y), ptr(stats), stream())
+    return y
+
+
+def groupnorm_silu_bwd(x0: Tensor, c0: int, x1: Optional[Tensor], c1: int, nb: int, hw: int, gamma: Tensor, beta: Tensor,
+                       stats: Tensor, silu: bool, dy: Tensor, dres: Optional[Tensor], res_ld: int, dx0: Tensor,
+                       dx1: Optional[Tensor], groups: int = 32) -> None:
+    assert dy.dtype == torch.bfloat16 and dx0.dtype == torch.bfloat16 and dy.numel() == nb * hw * (c0 + c1)
+    info = {"desc": f"nb{nb} hw{hw} c{c0}+{c1}", "bytes": 6.0 * nb * hw * (c0 + c1)} if _lib.PROFILE is not None else None
+    call("b200_groupnorm_silu_bwd", ptr(x0), c0, ptr(x1) if c1 else None, c1, nb, hw, groups, ptr(gamma), ptr(beta),
+         ptr(stats), int(silu), ptr(dy), ptr(dres), res_ld, ptr(dx0), ptr(dx1), stream(), info=info)
+
+
+def layernorm_bwd(x: Tensor, dy: Tensor, m: int, c: int, gamma: Tensor, eps: float, dres: Optional[Tensor],
+                  dx: Tensor) -> Tensor:
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and dx.dtype == torch.bfloat16
+    call("b200_layernorm_bwd", ptr(x), ptr(dy), m, c, ptr(gamma), float(eps), ptr(dres), ptr(dx), stream())
+    return dx
+
+
+def geglu_fwd(h: Tensor, m: int, f: int, out: Tensor) -> Tensor:
+    assert h.dtype == torch.bfloat16 and h.numel() == m * 2 * f and out.numel() == m * f
+    call("b200_geglu_fwd", ptr(h), m, f, ptr(out), stream())
+    return out
+
+
+def geglu_bwd(h: Tensor, dout: Tensor, m: int, f: int, dh: Tensor) -> Tensor:
+    assert h.dtype == torch.bfloat16 and dout.numel() == m * f and dh.numel() == m * 2 * f
+    call("b200_geglu_bwd", ptr(h), ptr(dout), m, f, ptr(dh), stream())
+    return dh
+
+
+def lora_wgrad(descs: Sequence["WgradDesc"], m: int) -> None:
+    arr = (WgradDesc * len(descs))(*descs)
+    call("b200_lora_wgrad", ctypes.cast(arr, ctypes.c_void_p), len(descs), m, stream())
+
+
+def zero_insert(dy: Tensor, nb: int, h: int, w: int, c: int, z: Tensor) -> Tensor:
+    assert dy.dtype == torch.bfloat16 and z.numel() == nb * h * w * c
+    call("b200_zero_insert", ptr(dy), nb, h, w, c, ptr(z), stream())
+    return z
+
+
+def upsample_nearest_bwd(dy: Tensor, nb: int, h: int, w: int, c: int, ho: int, wo: int, dx: Tensor) -> Tensor:
+    assert dy.dtype == torch.bfloat16 and dy.numel() == nb * ho * wo * c and dx.numel() == nb * h * w * c
+    call("b200_upsample_nearest_bwd", ptr(dy), nb, h, w, c, ho, wo, ptr(dx), stream())
+    return dx
+
+
+def add_bf16(y: Tensor, x: Tensor) -> Tensor:
+    assert y.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and y.numel() == x.numel()
+    call("b200_add_bf16", ptr(y), ptr(x), y.numel(), stream())
+    return y
+
+
+def mse_grad(pred_nhwc: Tensor, noise_nchw: Tensor, nb: int, hw: int, c_pad: int, inv_count: float, loss_sum: Tensor,
+             deps: Tensor) -> None:
+    assert pred_nhwc.dtype == torch.float32 and noise_nchw.dtype == torch.float32 and deps.dtype == torch.bfloat16
+    assert deps.numel() == nb * hw * c_pad and loss_sum.dtype == torch.float32
+    call("b200_mse_grad", ptr(pred_nhwc), ptr(noise_nchw), nb, hw, c_pad, float(inv_count), ptr(loss_sum), ptr(deps), stream())
+
+
+def lora_refresh(descs_dev: Tensor, n: int, flat: Tensor) -> None:
+    assert descs_dev.dtype == torch.uint8 and flat.dtype == torch.float32
+    call("b200_lora_refresh", ptr(descs_dev), n, ptr(flat), stream())
