@@ -47,6 +47,8 @@ _PROTOS = {
     "b200_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_float,
                                 c_float, c_int, c_float, c_void_p]),
     "b200_mse_partial": (c_int, [c_void_p, c_void_p, c_long, c_void_p, c_void_p]),
+    "b200_adamw_flat_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_float, c_float, c_float,
+                                    c_float, c_void_p]),
     # ---- fine-tuning step (forward variants that keep what the backward needs, and the backward kernels)
     "b200_attention_lse": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "b200_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -278,6 +278,26 @@ __global__ void adamw_flat_kernel(float* __restrict__ p, const float* __restrict
   }
 }
 
+// Same update with the per-step scalars {lr, bias-correction 1, bias-correction 2, grad_scale} read from device memory:
+// the launch is identical every step, so the whole training step can be one replayed CUDA graph.
+__global__ void adamw_flat_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                      float* __restrict__ v, size_t n, const float* __restrict__ hyper, float b1, float b2,
+                                      float eps, float wd) {
+  const float lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2], gs = hyper[3];
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float gr = g[i] * gs;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = b1 * m[i] + (1.0f - b1) * gr;
+    const float vi = b2 * v[i] + (1.0f - b2) * gr * gr;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi;
+  }
+}
+
 static inline int grid_for(size_t n, int block) {
   size_t g = (n + block - 1) / block;
   if (g > 148 * 8) g = 148 * 8;
@@ -378,5 +398,14 @@ extern "C" int b200_adamw_flat(float* param, const float* grad, float* m, float*
   adamw_flat_kernel<<<grid_for(static_cast<size_t>(n), 256), 256, 0, stream>>>(
       param, grad, m, v, static_cast<size_t>(n), lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
   B200_CHECK_LAUNCH("adamw_flat");
+  return B200_OK;
+}
+extern "C" int b200_adamw_flat_dev(float* param, const float* grad, float* m, float* v, long n, const float* hyper_dev,
+                                   float beta1, float beta2, float eps, float weight_decay, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(param && grad && m && v && hyper_dev && n > 0, "adamw_flat_dev: bad args");
+  adamw_flat_dev_kernel<<<grid_for(static_cast<size_t>(n), 256), 256, 0, stream>>>(
+      param, grad, m, v, static_cast<size_t>(n), hyper_dev, beta1, beta2, eps, weight_decay);
+  B200_CHECK_LAUNCH("adamw_flat_dev");
   return B200_OK;
 }

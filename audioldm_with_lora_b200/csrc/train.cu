@@ -379,6 +379,9 @@ struct WgradParams {
 };
 static constexpr int kWgThreads = 128;
 static constexpr int kWgRows = 64;      // rows staged per smem tile
+// CTA = 64 channels x r outputs over a slab of rows.  Thread = 8 channels x nj (<= 2) columns; for r < 16 the spare
+// thread groups take interleaved rows of the tile (row groups), so all 128 threads have work at rank 2 as at rank 32.
+// U is converted to fp32 once while it is staged; the inner loop is 2 LDS.128 + nj LDS.32 per 8 nj FMAs.
 __global__ void __launch_bounds__(kWgThreads)
 lora_wgrad_kernel(const WgradParams p) {
   pdl_launch_dependents();
@@ -388,25 +391,30 @@ lora_wgrad_kernel(const WgradParams p) {
   if (c0 >= d.C) return;
   const int m_begin = blockIdx.y * p.rows_per_cta;
   const int m_end = min(p.M, m_begin + p.rows_per_cta);
-  __shared__ __align__(16) __nv_bfloat16 sU[kWgRows][64];
+  __shared__ __align__(16) float sU[kWgRows][64];
   __shared__ __align__(16) float sV[kWgRows][32];
   const int tid = threadIdx.x;
-  const int c4 = (tid & 15) * 4;
-  const int jg = tid >> 4;                       // 0..7
-  const int nj = (d.r + 7) >> 3;                 // columns of V per thread (r <= 32)
-  float acc[4][4];
+  const int c8 = (tid & 7) * 8;
+  const int g = tid >> 3;                        // 0..15
+  int jgroups = 1;
+  while (jgroups < d.r && jgroups < 16) jgroups <<= 1;
+  const int nj = (d.r + jgroups - 1) / jgroups;  // 1 or 2
+  const int rowgroups = 16 / jgroups;
+  const int jg = g % jgroups, rg = g / jgroups;
+  const int j0 = jg * nj;
+  float acc[2][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int j = 0; j < 2; ++j)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
   for (int m0 = m_begin; m0 < m_end; m0 += kWgRows) {
-    // stage 64 rows x 64 channels of U (16-byte loads) and 64 rows x r of V (as fp32)
     for (int i = tid; i < kWgRows * 8; i += kWgThreads) {
       const int r = i >> 3, cv = (i & 7) * 8;
       const int m = m0 + r;
-      uint4 u = make_uint4(0, 0, 0, 0);
-      if (m < m_end && c0 + cv < d.C) u = *reinterpret_cast<const uint4*>(d.u + static_cast<size_t>(m) * d.ldu + c0 + cv);
-      *reinterpret_cast<uint4*>(&sU[r][cv]) = u;
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (m < m_end && c0 + cv < d.C) unpack8t(*reinterpret_cast<const uint4*>(d.u + static_cast<size_t>(m) * d.ldu + c0 + cv), f);
+      *reinterpret_cast<float4*>(&sU[r][cv]) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(&sU[r][cv + 4]) = make_float4(f[4], f[5], f[6], f[7]);
     }
     for (int i = tid; i < kWgRows * 32; i += kWgThreads) {
       const int r = i >> 5, j = i & 31;
@@ -415,30 +423,29 @@ lora_wgrad_kernel(const WgradParams p) {
     }
     __syncthreads();
 #pragma unroll 4
-    for (int r = 0; r < kWgRows; ++r) {
-      const uint2 uu = *reinterpret_cast<const uint2*>(&sU[r][c4]);
-      const float u0 = bf16_lo(uu.x), u1 = bf16_hi(uu.x), u2 = bf16_lo(uu.y), u3 = bf16_hi(uu.y);
+    for (int r = rg; r < kWgRows; r += rowgroups) {
+      const float4 ua = *reinterpret_cast<const float4*>(&sU[r][c8]);
+      const float4 ub = *reinterpret_cast<const float4*>(&sU[r][c8 + 4]);
+      const float u[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 2; ++j) {
         if (j < nj) {
-          const float vv = sV[r][jg * nj + j];
-          acc[0][j] = fmaf(u0, vv, acc[0][j]);
-          acc[1][j] = fmaf(u1, vv, acc[1][j]);
-          acc[2][j] = fmaf(u2, vv, acc[2][j]);
-          acc[3][j] = fmaf(u3, vv, acc[3][j]);
+          const float vv = sV[r][j0 + j];       // columns >= r are zero
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(u[i], vv, acc[j][i]);
         }
       }
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = c0 + c4 + i;
-    if (c >= d.C) continue;
+  for (int j = 0; j < 2; ++j) {
+    const int jj = j0 + j;
+    if (j >= nj || jj >= d.r) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int jj = jg * nj + j;
-      if (j < nj && jj < d.r) atomicAdd(d.out + static_cast<size_t>(c) * d.ldc + static_cast<size_t>(jj) * d.ldj, acc[i][j] * d.scale);
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + c8 + i;
+      if (c < d.C) atomicAdd(d.out + static_cast<size_t>(c) * d.ldc + static_cast<size_t>(jj) * d.ldj, acc[j][i] * d.scale);
     }
   }
 }
@@ -686,9 +693,9 @@ extern "C" int b200_lora_wgrad(const void* descs_host, int n, int m, void* strea
   }
   p.n = n;
   p.M = m;
-  // ~2 waves of CTAs over the token dimension
+  // ~8 resident CTAs per SM (128 threads, 24 KB smem each) over the token dimension
   const int cblk = (cmax + 63) / 64;
-  int chunks = (148 * 2 + cblk * n - 1) / (cblk * n);
+  int chunks = (148 * 8 + cblk * n - 1) / (cblk * n);
   int rows = (m + chunks - 1) / chunks;
   rows = (rows + kWgRows - 1) / kWgRows * kWgRows;
   if (rows < kWgRows) rows = kWgRows;

@@ -223,6 +223,9 @@ class UNet2DConditionModel(nn.Module):
         self.attn_modules = mods
         self._adapters: Dict[str, LoraEntry] = {}
         self.peft_config: Dict[str, LoraConfig] = {}
+        self._trainer = None                 # LoraTrainer bound to the adapter parameters (grad-mode forward)
+        self._trainer_synced = None
+        self.eval()                          # like diffusers' from_pretrained; the reference calls unet.train() (train:479)
 
     # ------------------------------------------------------------------ attention-processor API
     @property
@@ -272,6 +275,8 @@ class UNet2DConditionModel(nn.Module):
                 cur.to(cur.base_layer.weight.device)
             self._adapters[path] = e
         self.engine.set_lora(self._adapters, self.engine.lora_scale)
+        if not getattr(self, "_installing_from_trainer", False):
+            self._trainer = None             # adapters changed under the trainer: rebuild it on the next grad-mode call
 
     def add_adapter(self, adapter_config: LoraConfig, adapter_name: str = "default") -> None:
         if adapter_name in self.peft_config:
@@ -317,6 +322,55 @@ class UNet2DConditionModel(nn.Module):
         custom = {p: a for p, a in self._attn.items() if not isinstance(a.processor, B200AttnProcessor)}
         return custom or None
 
+    # ------------------------------------------------------------------ training seam (autograd-capable forward)
+    def _lora_linear(self, path: str) -> "LoraLinear":
+        attn_path, lin = path.rsplit(".to_", 1)
+        attn = self._attn[attn_path]
+        return attn.to_out[0] if lin == "out.0" else getattr(attn, "to_" + lin)
+
+    def lora_trainer(self, **kw):
+        """The LoraTrainer behind grad-mode `forward`: flat fp32 device arenas for the adapter parameters and their
+        gradients.  The peft-shaped `lora_A/lora_B[...].weight` Parameters become VIEWS into the parameter arena, so
+        `torch.optim.AdamW(filter(requires_grad, unet.parameters()))` (train_audioldm_lora.py:394-403) updates the
+        arena in place and `LoraTrainer`'s own fused optimizer sees the same memory."""
+        if self._trainer is None:
+            from .train import LoraTrainer
+            tr = LoraTrainer(self, **kw)
+            for path, (A, B) in tr.param_views().items():
+                lin = self._lora_linear(path)
+                name = "default" if "default" in lin.lora_A else next(iter(lin.lora_A))
+                lin.lora_A[name].weight.data = A
+                lin.lora_B[name].weight.data = B
+                lin.lora_A[name].weight.requires_grad_(True)
+                lin.lora_B[name].weight.requires_grad_(True)
+            self._trainer = tr
+        return self._trainer
+
+    def _trainer_params(self):
+        out = []
+        for path in self._trainer.slots:
+            lin = self._lora_linear(path)
+            name = "default" if "default" in lin.lora_A else next(iter(lin.lora_A))
+            out += [lin.lora_A[name].weight, lin.lora_B[name].weight]
+        return out
+
+    def _sync_from_trainer(self) -> None:
+        tr = self._trainer
+        if tr is None:
+            return
+        key = (tr.step_count, tr.flat_p._version)
+        if key != self._trainer_synced:
+            self._installing_from_trainer = True
+            try:
+                from .engine import LoraEntry
+                ad = {p: LoraEntry(A.detach().float().cpu().clone(), B.detach().float().cpu().clone(),
+                                   tr.slots[p].scaling * tr.slots[p].r) for p, (A, B) in tr.param_views().items()}
+                self._adapters.update(ad)
+                self.engine.set_lora(self._adapters, self.engine.lora_scale)
+            finally:
+                self._installing_from_trainer = False
+            self._trainer_synced = (tr.step_count, tr.flat_p._version)
+
     # ------------------------------------------------------------------ forward
     def _sync_engine_lora(self, scale: float) -> None:
         self.engine.set_lora_scale(scale)
@@ -332,11 +386,63 @@ class UNet2DConditionModel(nn.Module):
         if sample.dim() != 4 or sample.shape[1] != self.cfg.in_channels:
             raise ValueError(f"expected sample [B, {self.cfg.in_channels}, H, W], got {tuple(sample.shape)}")
         scale = float((cross_attention_kwargs or {}).get("scale", 1.0))
+        if self.training and torch.is_grad_enabled() and self._adapters and self.b200_device.type == "cuda" and \
+                self.custom_attn_processors() is None:
+            tr = self.lora_trainer()
+            params = self._trainer_params()
+            if any(p.requires_grad for p in params):
+                tr.lora_scale = scale
+                eps = _UNetLoraFunction.apply(self, sample, timestep, class_labels, *params).to(sample.dtype)
+                return UNet2DConditionOutput(sample=eps) if return_dict else (eps,)
+        self._sync_from_trainer()
         self._sync_engine_lora(scale)
         eps = self.engine.forward(sample, timestep, class_labels, attn_overrides=self.custom_attn_processors(),
                                   lora_scale=scale)
         eps = eps.to(sample.dtype)
         return UNet2DConditionOutput(sample=eps) if return_dict else (eps,)
+
+
+class _UNetLoraFunction(torch.autograd.Function):
+    """Grad-mode UNet forward: the B200 training forward now, the B200 backward walk when autograd asks for the
+    adapter gradients (`accelerator.backward(loss)`, train_audioldm_lora.py:557).  Inputs other than the LoRA
+    parameters get no gradient (the reference freezes everything else, train:373-376)."""
+
+    @staticmethod
+    def forward(ctx, unet, sample, timestep, class_labels, *params):
+        from .engine import LATENT_C_PAD
+        tr = unet._trainer
+        eng, dev = unet.engine, unet.b200_device
+        nb, c, h, w = sample.shape
+        x = sample.detach().to(dev, torch.float32).contiguous()
+        t = torch.as_tensor(timestep, dtype=torch.float32, device=dev).reshape(-1)
+        t = t.expand(nb).contiguous() if t.numel() == 1 else t.contiguous()
+        tr.refresh(nb, h, w)
+        xin = torch.zeros(nb, h * w, LATENT_C_PAD, dtype=torch.bfloat16, device=dev)
+        ops.pack_nchw_to_nhwc(x, nb, c, h * w, LATENT_C_PAD, xin)
+        silu_emb = torch.empty(nb, eng.cfg.temb_channels, dtype=torch.bfloat16, device=dev)
+        eng.embed(t, None, True, class_labels.detach().to(dev, torch.float32).contiguous(), None, silu_emb)
+        eps_nhwc = torch.empty(nb, h * w, eng.cfg.out_channels, dtype=torch.float32, device=dev)
+        ctx.b200 = (unet, tr.forward_train(xin, silu_emb, nb, h, w, eps_nhwc), (nb, h, w))
+        out = torch.empty(nb, eng.cfg.out_channels, h, w, dtype=torch.float32, device=dev)
+        ops.unpack_nhwc_to_nchw(eps_nhwc, nb, eng.cfg.out_channels, h * w, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        from .engine import LATENT_C_PAD
+        unet, fctx, (nb, h, w) = ctx.b200
+        tr = unet._trainer
+        deps = tr.arena.alloc((nb * h * w, LATENT_C_PAD), torch.bfloat16)
+        deps.zero_()
+        ops.pack_nchw_to_nhwc(d_out.detach().to(torch.float32).contiguous(), nb, d_out.shape[1], h * w, LATENT_C_PAD, deps)
+        saved = tr.flat_g.clone()            # autograd accumulates into .grad itself: hand it this call's gradients only
+        tr.flat_g.zero_()
+        tr.backward(fctx, deps)
+        grads = []
+        for a, b in tr.grad_views().values():
+            grads += [a.clone(), b.clone()]
+        tr.flat_g.copy_(saved)
+        return (None, None, None, None, *grads)
 
 
 def get_peft_model(unet: UNet2DConditionModel, config: LoraConfig, adapter_name: str = "default") -> UNet2DConditionModel:

@@ -226,6 +226,14 @@ def adamw_flat(param: Tensor, grad: Tensor, m: Tensor, v: Tensor, lr: float, bet
          step, grad_scale, stream())
 
 
+def adamw_flat_dev(param: Tensor, grad: Tensor, m: Tensor, v: Tensor, hyper: Tensor, beta1: float, beta2: float,
+                   eps: float, weight_decay: float) -> None:
+    """hyper: device fp32 [4] = {lr, 1 - beta1^t, 1 - beta2^t, grad_scale}."""
+    assert all(t.dtype == torch.float32 and t.is_contiguous() for t in (param, grad, m, v, hyper)) and hyper.numel() >= 4
+    call("b200_adamw_flat_dev", ptr(param), ptr(grad), ptr(m), ptr(v), param.numel(), ptr(hyper), beta1, beta2, eps,
+         weight_decay, stream())
+
+
 def mse_partial(pred: Tensor, target: Tensor, out_sum: Tensor) -> None:
     call("b200_mse_partial", ptr(pred), ptr(target), pred.numel(), ptr(out_sum), stream())
 

@@ -615,6 +615,71 @@ class LoraTrainer:
         ops.adamw_flat(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr, self.betas[0], self.betas[1], self.eps,
                        self.weight_decay, self.step_count, grad_scale)
 
+    # ------------------------------------------------------------------ the step as ONE replayed CUDA graph
+    def _hyper(self, grad_scale: float) -> Tensor:
+        t = self.step_count + 1
+        return torch.tensor([self.current_lr(), 1.0 - self.betas[0] ** t, 1.0 - self.betas[1] ** t, grad_scale],
+                            dtype=torch.float32)
+
+    def capture(self, nb: int, h: int, w: int = 16) -> None:
+        """Capture {add_noise, forward, loss, backward, gradient all-reduce, AdamW, LoRA refresh} for a fixed batch
+        shape into one CUDA graph.  Inputs are staged into static device buffers, the per-step optimizer scalars
+        (learning rate, bias corrections, 1/world) into a 4-float device vector -- nothing else changes between
+        steps, so `train_step_graphed` is: two tiny H2D copies + one graph launch, no host synchronisation."""
+        import torch.distributed as dist
+        dev, f32 = self.device, torch.float32
+        c = self.eng.cfg.in_channels
+        self._g_shape = (nb, h, w)
+        self._g_lat = torch.zeros(nb, c, h, w, dtype=f32, device=dev)
+        self._g_noise = torch.zeros_like(self._g_lat)
+        self._g_t = torch.zeros(nb, dtype=torch.long, device=dev)
+        self._g_emb = torch.zeros(nb, self.eng.cfg.class_in_dim, dtype=f32, device=dev)
+        self._g_hyper = torch.zeros(4, dtype=f32, device=dev)
+        self._g_loss = torch.zeros((), dtype=f32, device=dev)
+        world = dist.get_world_size(self.pg) if (dist.is_available() and dist.is_initialized()) else 1
+        self._g_world = world
+
+        def body():
+            noisy = torch.empty_like(self._g_lat)
+            ops.add_noise(self._g_lat, self._g_noise, self.sqrt_ac[self._g_t].contiguous(),
+                          self.sqrt_1mac[self._g_t].contiguous(), noisy)
+            self.flat_g.zero_()
+            loss = self.forward_backward(noisy, self._g_t, self._g_emb, self._g_noise)
+            self._g_loss.copy_(loss)
+            if world > 1:
+                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+            ops.adamw_flat_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self._g_hyper, self.betas[0],
+                               self.betas[1], self.eps, self.weight_decay)
+
+        # warm-up outside capture (packs weights, sizes the arena, sets function attributes) with the optimizer
+        # neutralised: lr = 0 and a state snapshot, so capture does not advance the model.
+        snap = [t.clone() for t in (self.flat_p, self.flat_m, self.flat_v)]
+        self._g_hyper.copy_(torch.tensor([0.0, 1.0, 1.0, 1.0]))
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            body()
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        for dst, src in zip((self.flat_p, self.flat_m, self.flat_v), snap):
+            dst.copy_(src)
+        self._graph = g
+
+    def train_step_graphed(self, latents: Tensor, noise: Tensor, timesteps: Tensor, prompt_embeds: Tensor) -> Tensor:
+        nb, _, h, w = latents.shape
+        if getattr(self, "_graph", None) is None or self._g_shape != (nb, h, w):
+            self.capture(nb, h, w)
+        self._g_lat.copy_(latents, non_blocking=True)
+        self._g_noise.copy_(noise, non_blocking=True)
+        self._g_t.copy_(timesteps, non_blocking=True)
+        self._g_emb.copy_(prompt_embeds, non_blocking=True)
+        self._g_hyper.copy_(self._hyper(1.0 / self._g_world), non_blocking=True)
+        self.step_count += 1
+        self._graph.replay()
+        return self._g_loss
+
     def train_step(self, latents: Tensor, noise: Tensor, timesteps: Tensor, prompt_embeds: Tensor) -> Tensor:
         """One optimizer step on this rank's batch (train_audioldm_lora.py:499-565 with synthetic latents / embeddings)."""
         dev = self.device

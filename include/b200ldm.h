@@ -115,6 +115,77 @@ int b200_add_noise(const float* x0, const float* noise, const float* sqrt_ac, co
 int b200_adamw_flat(float* param, const float* grad, float* m, float* v, long n, float lr, float beta1, float beta2,
                     float eps, float weight_decay, int step, float grad_scale, void* stream);
 int b200_mse_partial(const float* pred, const float* target, long n, float* out_sum, void* stream);
+/* b200_adamw_flat with the per-step scalars in device memory: hyper_dev = {lr, 1 - beta1^t, 1 - beta2^t, grad_scale}
+ * (so a captured CUDA graph of the training step stays valid while the LR schedule advances). */
+int b200_adamw_flat_dev(float* param, const float* grad, float* m, float* v, long n, const float* hyper_dev,
+                        float beta1, float beta2, float eps, float weight_decay, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fine-tuning step: the forward forms that keep what the backward pass needs, and the
+ * backward kernels.  Together they replace torch autograd under `accelerator.backward(loss)`
+ * (/root/reference/script/train/train_audioldm_lora.py:557) for the frozen-base / LoRA-only setting of
+ * train_audioldm_lora.py:373-385: activation gradients (dgrad) + rank-r weight gradients.  dgrad of every
+ * conv / linear layer is b200_conv_gemm itself with transposed, tap-flipped packed weights.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* b200_attention that also writes lse fp32 [batch, heads, seq]: log2-domain log-sum-exp of the scaled scores. */
+int b200_attention_lse(const void* qkv, void* out, float* lse, int batch, int seq, int heads, int head_dim,
+                       float scale, void* stream);
+
+/* Flash-attention backward on tcgen05: d[Q|K|V] (bf16 [batch, seq, 3C], same fused layout as qkv) from
+ * qkv, o = attention output, dout = its gradient (bf16 [batch, seq, C]) and lse.  delta fp32 [batch, heads,
+ * seq] is scratch (rowsum(dout * o), written here).  Two launches of one kernel (a key-block pass for dK/dV and a
+ * query-block pass for dQ): every output element has one writer, no atomics.  head_dim 32/48/64/80/96.
+ * Replaces the autograd backward of F.scaled_dot_product_attention. */
+int b200_attention_bwd(const void* qkv, const void* o, const void* dout, const float* lse, float* delta, void* dqkv,
+                       int batch, int seq, int heads, int head_dim, float scale, void* stream);
+
+/* b200_groupnorm_silu that also writes stats fp32 [nb, groups, 2] = (mean, rstd). */
+int b200_groupnorm_silu_stats(const void* x0, int c0, const void* x1, int c1, int nb, int hw, int groups,
+                              const float* gamma, const float* beta, float eps, int silu, void* y, float* stats,
+                              void* stream);
+
+/* d/dx of SiLU(GroupNorm(cat(x0, x1))) (silu = 0: GroupNorm only): dx0 [nb*hw, c0], dx1 [nb*hw, c1] (nullable: the
+ * skip's gradient is not needed) from dy [nb*hw, c0+c1]; dres (nullable, row stride res_ld, concatenated channel c at
+ * column c) is added -- the residual / shortcut path of ResnetBlock2D and Transformer2DModel.  Frozen affine: no
+ * dgamma / dbeta.  Replaces the autograd backward of F.group_norm + F.silu. */
+int b200_groupnorm_silu_bwd(const void* x0, int c0, const void* x1, int c1, int nb, int hw, int groups,
+                            const float* gamma, const float* beta, const float* stats, int silu, const void* dy,
+                            const void* dres, int res_ld, void* dx0, void* dx1, void* stream);
+
+/* d/dx of LayerNorm over [m, c] (+ dres, the residual-stream gradient).  Statistics are recomputed from x. */
+int b200_layernorm_bwd(const void* x, const void* dy, int m, int c, const float* gamma, float eps, const void* dres,
+                       void* dx, void* stream);
+
+/* GEGLU with the pre-activation kept: h bf16 [m, 2f] = [values | gates] -> out [m, f] = v * gelu_erf(g);
+ * backward: dh [m, 2f] from dout [m, f] and h.  (Inference fuses GEGLU into the GEMM epilogue instead.) */
+int b200_geglu_fwd(const void* h, long m, int f, void* out, void* stream);
+int b200_geglu_bwd(const void* h, const void* dout, long m, int f, void* dh, void* stream);
+
+/* LoRA weight gradients (peft lora.Linear: y = base(x) + s * B A x): for each of n <= 8 descriptors
+ *   out[c*ldc + j*ldj] += scale * sum_{row < m} U[row, c] * V[row, j]        (c < C, j < r <= 32)
+ * dB [Cout, r] = s dY^T T (U = dY, V = T = x A^T, ldc = r, ldj = 1);  dA [r, Cin] = dT^T x (U = x, V = dT = s dY B,
+ * ldc = 1, ldj = Cin).  `out` points into the flat fp32 LoRA-gradient arena that NCCL all-reduces (DDP, C1).
+ * descs_host: HOST array of struct { const void* u; const void* v; float* out; int ldu, ldv, C, r, ldc, ldj;
+ * float scale; } (u, v bf16 device pointers, leading dims in elements). */
+int b200_lora_wgrad(const void* descs_host, int n, int m, void* stream);
+
+/* Data movement of the backward walk: z[n, 2i, 2j, :] = dy[n, i, j, :] else 0 (the stride-2 Downsample2D dgrad
+ * becomes a stride-1 dgrad over z [nb, h, w, c]); gradient of the nearest-neighbour resize; y += x (bf16). */
+int b200_zero_insert(const void* dy, int nb, int h, int w, int c, void* z, void* stream);
+int b200_upsample_nearest_bwd(const void* dy, int nb, int h, int w, int c, int ho, int wo, void* dx, void* stream);
+int b200_add_bf16(void* y, const void* x, long n, void* stream);
+
+/* F.mse_loss(pred, noise, "mean") and its gradient (train_audioldm_lora.py:549): *loss_sum += sum (pred - noise)^2;
+ * deps bf16 [nb*hw, c_pad] = 2 (pred - noise) * inv_count in columns 0..7, zero elsewhere.  pred fp32 NHWC
+ * [nb, hw, 8], noise fp32 NCHW [nb, 8, hw]. */
+int b200_mse_grad(const float* pred_nhwc, const float* noise_nchw, int nb, int hw, int c_pad, float inv_count,
+                  float* loss_sum, void* deps, void* stream);
+
+/* After optimizer.step(): rewrite the bf16 packed LoRA operands from the flat fp32 parameter arena.  descs_dev: DEVICE
+ * array of n records struct { void* dst; long long src_off; int dst_ld, src_rows, src_cols, transpose; float scale;
+ * int pad; }: dst block = scale * (transpose ? src^T : src), src = flat + src_off as [src_rows, src_cols]. */
+int b200_lora_refresh(const void* descs_dev, int n, const float* flat, void* stream);
 
 #ifdef __cplusplus
 }

@@ -137,3 +137,50 @@ def test_zero_B_gives_zero_A_grad_and_full_size_step_is_finite():
     a_norm = sum(float(a.norm()) for a, _ in g.values())
     b_norm = sum(float(b.norm()) for _, b in g.values())
     assert a_norm == 0.0 and b_norm > 0.0
+
+
+def test_reference_shaped_training_loop_through_autograd():
+    """The reference's own loop shape (train_audioldm_lora.py:373-403, 479, 539-565): get_peft_model, AdamW over
+    filter(requires_grad), unet.train(), unet(...)[0], F.mse_loss, loss.backward(), optimizer.step() -- with torch's
+    optimizer and autograd driving the B200 forward / backward through the autograd.Function seam."""
+    import torch.nn.functional as F
+    import audioldm_with_lora_b200 as b2
+    from audioldm_with_lora_b200 import synthetic
+    from oracle import train_ref, unet_ref
+    cfg = b2.CONFIGS["S"]
+    sd = synthetic.random_unet_state_dict(cfg, seed=0)
+    lsd = synthetic.random_lora_state_dict(cfg, 8, fmt="peft")
+    unet = b2.UNet2DConditionModel(cfg, sd, device=DEV)
+    unet.load_state_dict(lsd, strict=False)
+    ad = b2.parse_lora_state_dict(lsd)
+    kw = dict(lr=1e-3, weight_decay=1e-2)
+    ref = train_ref.TrainRef(sd, unet_ref.ARCH_S, {k: (e.A, e.B, e.alpha) for k, e in ad.items()}, **kw)
+    unet.requires_grad_(False)
+    tr = unet.lora_trainer()                      # binds the peft-shaped parameters to the flat device arena
+    lora_layers = [p for p in unet.parameters() if p.requires_grad]
+    assert len(lora_layers) == 2 * len(tr.slots) and all(p.is_cuda for p in lora_layers)
+    opt = torch.optim.AdamW(lora_layers, betas=(0.9, 0.999), eps=1e-8, **kw)
+    unet.train()
+    p0 = tr.flat_p.cpu().clone()
+    for step in range(2):
+        lat, noise, t, emb = _batch(2, 32, seed=40 + step)
+        noisy = ref.noise_sched.add_noise(lat, noise, t)
+        pred = unet(noisy.to(DEV), t.to(DEV), encoder_hidden_states=None, class_labels=emb.to(DEV),
+                    cross_attention_kwargs={"scale": 1.0}, return_dict=False)[0]
+        loss = F.mse_loss(pred.float(), noise.to(DEV).float(), reduction="mean")
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        loss_ref = ref.train_step(lat, noise, t, emb)
+        assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < 2e-2
+    upd, upd_ref = tr.flat_p.cpu() - p0, _flat(ref, tr, "param") - p0
+    cos = torch.dot(upd, upd_ref) / (upd.norm() * upd_ref.norm())
+    assert cos > 0.98, f"update cosine {cos:.4f}"
+    # back to inference: eval + no_grad picks the updated adapters up
+    unet.eval()
+    lat, _, t, emb = _batch(2, 32, seed=98)
+    with torch.no_grad():
+        eps = unet(lat.to(DEV), 300, class_labels=emb.to(DEV), return_dict=False)[0]
+        lora = unet_ref.LoraSet({p: (A.detach(), B.detach(), al) for p, (A, B, al) in ref.params.items()})
+        eps_ref = unet_ref.unet_forward(ref.sd, unet_ref.ARCH_S, lat, 300, emb, lora=lora)
+    assert rel(eps, eps_ref) < 3e-2
