@@ -90,17 +90,14 @@ class LoraTrainer:
             e = self.eng.lora[path]
             host[s.off_a: s.off_a + s.r * s.c] = e.A.float().reshape(-1)
             host[s.off_b: s.off_b + s.r * s.c] = e.B.float().reshape(-1)
-        if self.device.type == "cuda":
-            self.flat_p = host.to(self.device)
-            self.flat_g = torch.zeros_like(self.flat_p)
-            self.flat_m = torch.zeros_like(self.flat_p)
-            self.flat_v = torch.zeros_like(self.flat_p)
-            self.loss_sum = torch.zeros(1, dtype=torch.float32, device=self.device)
-            ac = self.sched.alphas_cumprod.to(self.device, torch.float32)
-            self.sqrt_ac, self.sqrt_1mac = ac.sqrt().contiguous(), (1 - ac).sqrt().contiguous()
-        else:
-            self.flat_p = host
-            self.flat_g = torch.zeros_like(host)
+        # (a CPU device only occurs in the host-logic tests, where tests/fake_ops.py stands in for the kernels)
+        self.flat_p = host.to(self.device)
+        self.flat_g = torch.zeros_like(self.flat_p)
+        self.flat_m = torch.zeros_like(self.flat_p)
+        self.flat_v = torch.zeros_like(self.flat_p)
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=self.device)
+        ac = self.sched.alphas_cumprod.to(self.device, torch.float32)
+        self.sqrt_ac, self.sqrt_1mac = ac.sqrt().contiguous(), (1 - ac).sqrt().contiguous()
         self._tplans: Dict[Tuple[int, int, int], dict] = {}
         self.arena: Optional[Arena] = None
         self.first_tfm = self._first_adapted_tfm()
@@ -225,12 +222,9 @@ class LoraTrainer:
         descs = np.zeros(len(refresh), dtype=ops.REFRESH_DTYPE)
         for i, (dst, row, col, src_off, sr, scn, tr, scale) in enumerate(refresh):
             ld = dst.shape[1]
-            base = dst.data_ptr() if dst.is_cuda else 0
-            descs[i] = (base + (row * ld + col) * 2, src_off, ld, sr, scn, tr, scale, 0)
-        tp = {"Wb": Wb, "refresh_host": refresh, "refresh_n": len(refresh), "weights_version": eng.weights_version}
-        if self.device.type == "cuda":
-            tp["refresh_dev"] = torch.from_numpy(descs.view(np.uint8).copy()).to(self.device)
-        return tp
+            descs[i] = (dst.data_ptr() + (row * ld + col) * 2, src_off, ld, sr, scn, tr, scale, 0)
+        return {"Wb": Wb, "refresh_host": refresh, "refresh_n": len(refresh), "weights_version": eng.weights_version,
+                "refresh_dev": torch.from_numpy(descs.view(np.uint8).copy()).to(self.device)}
 
     def refresh(self, nb: int, h: int, w: int) -> None:
         """bf16 packed LoRA operands (forward + backward) <- flat fp32 parameters: one launch."""
@@ -615,18 +609,12 @@ class LoraTrainer:
         ops.adamw_flat(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr, self.betas[0], self.betas[1], self.eps,
                        self.weight_decay, self.step_count, grad_scale)
 
-    # ------------------------------------------------------------------ the step as ONE replayed CUDA graph
-    def _hyper(self, grad_scale: float) -> Tensor:
-        t = self.step_count + 1
-        return torch.tensor([self.current_lr(), 1.0 - self.betas[0] ** t, 1.0 - self.betas[1] ** t, grad_scale],
-                            dtype=torch.float32)
-
+    # ------------------------------------------------------------------ the step as a replayed CUDA graph
     def capture(self, nb: int, h: int, w: int = 16) -> None:
-        """Capture {add_noise, forward, loss, backward, gradient all-reduce, AdamW, LoRA refresh} for a fixed batch
-        shape into one CUDA graph.  Inputs are staged into static device buffers, the per-step optimizer scalars
-        (learning rate, bias corrections, 1/world) into a 4-float device vector -- nothing else changes between
-        steps, so `train_step_graphed` is: two tiny H2D copies + one graph launch, no host synchronisation."""
-        import torch.distributed as dist
+        """Capture {LoRA refresh, add_noise, forward, loss, backward} for a fixed batch shape into one CUDA graph (about
+        1000 kernel launches).  Inputs are staged into static device buffers.  The gradient all-reduce (NCCL) and the
+        fused AdamW launch stay outside the graph: two host-side launches per step, and the collective never runs under
+        stream capture."""
         dev, f32 = self.device, torch.float32
         c = self.eng.cfg.in_channels
         self._g_shape = (nb, h, w)
@@ -634,27 +622,16 @@ class LoraTrainer:
         self._g_noise = torch.zeros_like(self._g_lat)
         self._g_t = torch.zeros(nb, dtype=torch.long, device=dev)
         self._g_emb = torch.zeros(nb, self.eng.cfg.class_in_dim, dtype=f32, device=dev)
-        self._g_hyper = torch.zeros(4, dtype=f32, device=dev)
         self._g_loss = torch.zeros((), dtype=f32, device=dev)
-        world = dist.get_world_size(self.pg) if (dist.is_available() and dist.is_initialized()) else 1
-        self._g_world = world
 
         def body():
             noisy = torch.empty_like(self._g_lat)
             ops.add_noise(self._g_lat, self._g_noise, self.sqrt_ac[self._g_t].contiguous(),
                           self.sqrt_1mac[self._g_t].contiguous(), noisy)
             self.flat_g.zero_()
-            loss = self.forward_backward(noisy, self._g_t, self._g_emb, self._g_noise)
-            self._g_loss.copy_(loss)
-            if world > 1:
-                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
-            ops.adamw_flat_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self._g_hyper, self.betas[0],
-                               self.betas[1], self.eps, self.weight_decay)
+            self._g_loss.copy_(self.forward_backward(noisy, self._g_t, self._g_emb, self._g_noise))
 
-        # warm-up outside capture (packs weights, sizes the arena, sets function attributes) with the optimizer
-        # neutralised: lr = 0 and a state snapshot, so capture does not advance the model.
-        snap = [t.clone() for t in (self.flat_p, self.flat_m, self.flat_v)]
-        self._g_hyper.copy_(torch.tensor([0.0, 1.0, 1.0, 1.0]))
+        # warm-up outside capture: packs weights, sizes the arena, sets function attributes (no optimizer step)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -663,11 +640,11 @@ class LoraTrainer:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             body()
-        for dst, src in zip((self.flat_p, self.flat_m, self.flat_v), snap):
-            dst.copy_(src)
         self._graph = g
 
     def train_step_graphed(self, latents: Tensor, noise: Tensor, timesteps: Tensor, prompt_embeds: Tensor) -> Tensor:
+        """train_step with the forward/backward replayed from a CUDA graph.  Returns the loss buffer (a static device
+        tensor that the next step overwrites)."""
         nb, _, h, w = latents.shape
         if getattr(self, "_graph", None) is None or self._g_shape != (nb, h, w):
             self.capture(nb, h, w)
@@ -675,9 +652,8 @@ class LoraTrainer:
         self._g_noise.copy_(noise, non_blocking=True)
         self._g_t.copy_(timesteps, non_blocking=True)
         self._g_emb.copy_(prompt_embeds, non_blocking=True)
-        self._g_hyper.copy_(self._hyper(1.0 / self._g_world), non_blocking=True)
-        self.step_count += 1
         self._graph.replay()
+        self.optimizer_step(self.allreduce_grads())
         return self._g_loss
 
     def train_step(self, latents: Tensor, noise: Tensor, timesteps: Tensor, prompt_embeds: Tensor) -> Tensor:

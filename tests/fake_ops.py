@@ -161,9 +161,170 @@ def mse_partial(pred, target, out_sum):
     out_sum += ((pred - target) ** 2).sum()
 
 
+# ------------------------------------------------------------------------------------------ fine-tuning step
+def _from_ptr(ptr, n, dtype):
+    """A torch view of `n` elements of CPU memory at address `ptr` (the descriptor-table kernels take raw pointers)."""
+    import ctypes
+    import numpy as np
+    if dtype == bf16:
+        buf = (ctypes.c_uint16 * n).from_address(ptr)
+        return torch.from_numpy(np.frombuffer(buf, dtype=np.uint16)).view(bf16)
+    buf = (ctypes.c_float * n).from_address(ptr)
+    return torch.from_numpy(np.frombuffer(buf, dtype=np.float32))
+
+
+def attention_lse(qkv, out, lse, batch, seq, heads, head_dim, scale=None):
+    scale = head_dim ** -0.5 if scale is None else scale
+    q, k, v = [t.view(batch, seq, heads, head_dim).transpose(1, 2).float()
+               for t in qkv.view(batch, seq, -1).chunk(3, -1)]
+    s = (q @ k.transpose(-1, -2)) * scale
+    lse.view(batch, heads, seq).copy_(torch.logsumexp(s, -1) * 1.4426950408889634)
+    o = torch.softmax(s, -1) @ v
+    out.view(batch, seq, heads * head_dim).copy_(o.transpose(1, 2).reshape(batch, seq, -1).to(bf16))
+    return out
+
+
+def attention_bwd(qkv, o, dout, lse, delta, dqkv, batch, seq, heads, head_dim, scale=None):
+    scale = head_dim ** -0.5 if scale is None else scale
+    C = heads * head_dim
+    q, k, v = [t.view(batch, seq, heads, head_dim).transpose(1, 2).float()
+               for t in qkv.view(batch, seq, -1).chunk(3, -1)]
+    do = dout.view(batch, seq, heads, head_dim).transpose(1, 2).float()
+    of = o.view(batch, seq, heads, head_dim).transpose(1, 2).float()
+    d = (do * of).sum(-1)
+    delta.view(batch, heads, seq).copy_(d)
+    p = torch.exp2((q @ k.transpose(-1, -2)) * scale * 1.4426950408889634 - lse.view(batch, heads, seq, 1))
+    dv = p.transpose(-1, -2) @ do
+    ds = p * (do @ v.transpose(-1, -2) - d[..., None])
+    dq, dk = (ds @ k) * scale, (ds.transpose(-1, -2) @ q) * scale
+    out = torch.cat([t.transpose(1, 2).reshape(batch, seq, C) for t in (dq, dk, dv)], -1)
+    dqkv.view(batch, seq, 3 * C).copy_(out.to(bf16))
+    return dqkv
+
+
+def groupnorm_silu_stats(x0, c0, x1, c1, nb, hw, gamma, beta, eps, silu, y, stats, groups=32):
+    groupnorm_silu(x0, c0, x1, c1, nb, hw, gamma, beta, eps, silu, y, groups)
+    x = x0.view(nb, hw, c0).float()
+    if c1:
+        x = torch.cat([x, x1.view(nb, hw, c1).float()], -1)
+    xg = x.view(nb, hw, groups, -1).permute(0, 2, 1, 3).reshape(nb, groups, -1)
+    st = stats.view(nb, groups, 2)
+    st[..., 0] = xg.mean(-1)
+    st[..., 1] = (xg.var(-1, unbiased=False) + eps).rsqrt()
+    return y
+
+
+def groupnorm_silu_bwd(x0, c0, x1, c1, nb, hw, gamma, beta, stats, silu, dy, dres, res_ld, dx0, dx1, groups=32):
+    """Closed form from the SAVED statistics (what the kernel does), not autograd of F.group_norm."""
+    C = c0 + c1
+    cpg = C // groups
+    x = x0.view(nb, hw, c0).float()
+    if c1:
+        x = torch.cat([x, x1.view(nb, hw, c1).float()], -1)
+    st = stats.view(nb, groups, 2)
+    mean = st[..., 0].repeat_interleave(cpg, 1)[:, None, :]
+    rstd = st[..., 1].repeat_interleave(cpg, 1)[:, None, :]
+    xh = (x - mean) * rstd
+    g = dy.view(nb, hw, C).float()
+    if silu:
+        yh = xh * gamma + beta
+        sg = torch.sigmoid(yh)
+        g = g * sg * (1 + yh * (1 - sg))
+    dxh = g * gamma
+    m1 = dxh.view(nb, hw, groups, cpg).mean((1, 3)).repeat_interleave(cpg, 1)[:, None, :]
+    m2 = (dxh * xh).view(nb, hw, groups, cpg).mean((1, 3)).repeat_interleave(cpg, 1)[:, None, :]
+    gx = rstd * (dxh - m1 - xh * m2)
+    if dres is not None:
+        gx = gx + dres.view(nb, hw, res_ld)[:, :, :C].float()
+    dx0.view(nb, hw, c0).copy_(gx[..., :c0].to(bf16))
+    if dx1 is not None:
+        dx1.view(nb, hw, c1).copy_(gx[..., c0:].to(bf16))
+
+
+def layernorm_bwd(x, dy, m, c, gamma, eps, dres, dx):
+    xr = x.view(m, c).float().requires_grad_(True)
+    F.layer_norm(xr, (c,), gamma, torch.zeros_like(gamma), eps).backward(dy.view(m, c).float())
+    g = xr.grad + (dres.view(m, c).float() if dres is not None else 0.0)
+    dx.view(m, c).copy_(g.to(bf16))
+    return dx
+
+
+def geglu_fwd(h, m, f, out):
+    val, gate = h.view(m, 2 * f).float().chunk(2, -1)
+    out.view(m, f).copy_((val * F.gelu(gate)).to(bf16))
+    return out
+
+
+def geglu_bwd(h, dout, m, f, dh):
+    hr = h.view(m, 2 * f).float().requires_grad_(True)
+    val, gate = hr.chunk(2, -1)
+    (val * F.gelu(gate)).backward(dout.view(m, f).float())
+    dh.view(m, 2 * f).copy_(hr.grad.to(bf16))
+    return dh
+
+
+def lora_wgrad(descs, m):
+    for d in descs:
+        u = _from_ptr(d.u, (m - 1) * d.ldu + d.C, bf16).float()
+        v = _from_ptr(d.v, (m - 1) * d.ldv + d.r, bf16).float()
+        U = torch.as_strided(u, (m, d.C), (d.ldu, 1))
+        V = torch.as_strided(v, (m, d.r), (d.ldv, 1))
+        G = (U.T @ V) * d.scale                                   # [C, r]
+        span = (d.C - 1) * d.ldc + (d.r - 1) * d.ldj + 1
+        out = torch.as_strided(_from_ptr(d.out, span, torch.float32), (d.C, d.r), (d.ldc, d.ldj))
+        out += G
+
+
+def zero_insert(dy, nb, h, w, c, z):
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    zz = z.view(nb, h, w, c)
+    zz.zero_()
+    zz[:, ::2, ::2] = dy.view(nb, ho, wo, c)
+    return z
+
+
+def upsample_nearest_bwd(dy, nb, h, w, c, ho, wo, dx):
+    xr = torch.zeros(nb, c, h, w, requires_grad=True)
+    F.interpolate(xr, size=(ho, wo), mode="nearest").backward(dy.view(nb, ho, wo, c).float().permute(0, 3, 1, 2))
+    dx.view(nb, h, w, c).copy_(xr.grad.permute(0, 2, 3, 1).to(bf16))
+    return dx
+
+
+def add_bf16(y, x):
+    y.copy_((y.float() + x.float()).to(bf16))
+    return y
+
+
+def mse_grad(pred_nhwc, noise_nchw, nb, hw, c_pad, inv_count, loss_sum, deps):
+    diff = pred_nhwc.view(nb, hw, 8) - noise_nchw.view(nb, 8, hw).permute(0, 2, 1)
+    loss_sum += (diff ** 2).sum()
+    d = deps.view(nb, hw, c_pad)
+    d.zero_()
+    d[..., :8] = (2 * diff * inv_count).to(bf16)
+
+
+def lora_refresh(descs_dev, n, flat):
+    import numpy as np
+    from audioldm_with_lora_b200.ops import REFRESH_DTYPE
+    recs = np.frombuffer(descs_dev.numpy().tobytes(), dtype=REFRESH_DTYPE)
+    for r in recs[:n]:
+        sr, sc, ld = int(r["src_rows"]), int(r["src_cols"]), int(r["dst_ld"])
+        src = flat[int(r["src_off"]): int(r["src_off"]) + sr * sc].view(sr, sc) * float(r["scale"])
+        if r["transpose"]:
+            src = src.t()
+        rows, cols = src.shape
+        dst = torch.as_strided(_from_ptr(int(r["dst"]), (rows - 1) * ld + cols, bf16), (rows, cols), (ld, 1))
+        dst.copy_(src.to(bf16))
+
+
+TRAIN_OPS = ("attention_lse", "attention_bwd", "groupnorm_silu_stats", "groupnorm_silu_bwd", "layernorm_bwd",
+             "geglu_fwd", "geglu_bwd", "lora_wgrad", "zero_insert", "upsample_nearest_bwd", "add_bf16", "mse_grad",
+             "lora_refresh")
+
+
 def install(monkeypatch, ops_module):
     """Replace the kernel wrappers of `ops_module` (keeps PackedWeight / tiling helpers)."""
     for name in ("conv_gemm", "groupnorm_silu", "layernorm", "attention", "time_class_embed",
                  "pack_nchw_to_nhwc", "unpack_nhwc_to_nchw", "upsample_nearest", "sampler_step", "add_noise",
-                 "adamw_flat", "mse_partial"):
+                 "adamw_flat", "mse_partial") + TRAIN_OPS:
         monkeypatch.setattr(ops_module, name, globals()[name])

@@ -1,0 +1,163 @@
+"""CPU tests of the fine-tuning step's HOST logic (kernels emulated by tests/fake_ops.py): flat-arena layout, the
+LoRA refresh table, the backward walk over the UNet graph, DDP gradient averaging over a 2-rank gloo group -- against
+the fp32 autograd oracle (oracle/train_ref.py)."""
+import os
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parents[1]
+TINY = (64, 128, 192, 256)
+
+
+def _install_fakes():
+    from audioldm_with_lora_b200 import ops
+    from tests import fake_ops
+    for name in ("conv_gemm", "groupnorm_silu", "layernorm", "attention", "time_class_embed", "pack_nchw_to_nhwc",
+                 "unpack_nhwc_to_nchw", "upsample_nearest", "sampler_step", "add_noise", "adamw_flat",
+                 "mse_partial") + fake_ops.TRAIN_OPS:
+        setattr(ops, name, getattr(fake_ops, name))
+
+
+def _tiny(rank=4, targets=("to_q", "to_k", "to_v", "to_out.0"), **kw):
+    import audioldm_with_lora_b200 as b2
+    from audioldm_with_lora_b200 import synthetic
+    from audioldm_with_lora_b200.arch import UNetConfig
+    from audioldm_with_lora_b200.train import LoraTrainer
+    from oracle import train_ref, unet_ref
+    cfg = UNetConfig("tiny", TINY)
+    sd = synthetic.random_unet_state_dict(cfg, seed=0)
+    lsd = synthetic.random_lora_state_dict(cfg, rank, targets=targets, fmt="peft")
+    unet = b2.UNet2DConditionModel(cfg, sd, device="cpu")
+    unet.load_state_dict(lsd, strict=False)
+    ad = b2.parse_lora_state_dict(lsd)
+    spec = unet_ref.UNetSpec(block_out_channels=TINY, time_proj_dim=TINY[0])
+    trainer = LoraTrainer(unet, **kw)
+    ref = train_ref.TrainRef(sd, spec, {k: (e.A, e.B, e.alpha) for k, e in ad.items()}, **kw)
+    return unet, trainer, ref
+
+
+def _batch(nb, h, seed):
+    from audioldm_with_lora_b200 import synthetic
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(nb, 8, h, 16, generator=g), torch.randn(nb, 8, h, 16, generator=g),
+            torch.randint(0, 1000, (nb,), generator=g), synthetic.clap_embeddings(nb)[0])
+
+
+def _flat(ref, trainer, what):
+    out = torch.zeros(trainer.numel)
+    for p, s in trainer.slots.items():
+        A, B, _ = ref.params[p]
+        a, b = (A.grad, B.grad) if what == "grad" else (A.detach(), B.detach())
+        out[s.off_a: s.off_a + s.r * s.c] = a.reshape(-1)
+        out[s.off_b: s.off_b + s.r * s.c] = b.reshape(-1)
+    return out
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
+
+
+def test_flat_layout_and_refresh_table(fake_kernels):
+    """The refresh kernel's descriptor table must reproduce exactly what the engine packs from the same adapters
+    (forward operands), and the transposed counterparts (backward operands)."""
+    unet, trainer, _ = _tiny(rank=4, targets=("to_q", "to_v", "to_out.0"))
+    n_ad = len(trainer.slots)
+    assert trainer.numel == sum(2 * s.r * s.c for s in trainer.slots.values())
+    offs = sorted((s.off_a, s.off_b) for s in trainer.slots.values())
+    assert offs[0][0] == 0 and all(b == a + s for (a, b), s in zip(offs, [trainer.slots[p].r * trainer.slots[p].c
+                                                                    for p in trainer.slots]))
+    nb, h, w = 2, 16, 16
+    plan = unet.engine._plan(nb, h, w)
+    before = {k: v.w.clone() for k, v in plan["W"].items()}
+    tp = trainer._tplan(nb, h, w)
+    assert tp["refresh_n"] == 4 * n_ad
+    trainer.refresh(nb, h, w)                           # flat_p was initialised from the same adapters: a no-op
+    for k, v in plan["W"].items():
+        assert torch.equal(v.w, before[k]), k
+    # backward operands: K segment = A^T, down-projection = (s B)^T
+    p = next(iter(trainer.slots)).rsplit(".to_", 1)[0]
+    c = trainer.slots[p + ".to_q"].c
+    A_q, B_q = trainer.param_views()[p + ".to_q"]
+    wq = tp["Wb"][p + ".bwd_qkv"].w
+    assert torch.equal(wq[:c, 3 * c: 3 * c + 4], A_q.t().to(torch.bfloat16))
+    assert torch.equal(tp["Wb"][p + ".bwd_down_qkv"].w[:4, :c], B_q.t().to(torch.bfloat16))
+    # a parameter update flows into every packed operand
+    trainer.flat_p.mul_(2.0)
+    old = wq[:c, 3 * c: 3 * c + 4].clone()
+    assert not torch.equal(old, A_q.t().to(torch.bfloat16))          # A_q is a view of flat_p: already doubled
+    trainer.refresh(nb, h, w)
+    assert torch.equal(wq[:c, 3 * c: 3 * c + 4], A_q.t().to(torch.bfloat16))
+    assert torch.equal(plan["W"][p + ".lora_down_qkv"].w[:4], A_q.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("rank,targets,nb,h", [(4, ("to_q", "to_k", "to_v", "to_out.0"), 2, 16),
+                                               (2, ("to_q", "to_v"), 1, 12)])
+def test_backward_walk_matches_autograd_oracle(fake_kernels, rank, targets, nb, h):
+    unet, trainer, ref = _tiny(rank, targets)
+    lat, noise, t, emb = _batch(nb, h, seed=5)
+    loss_ref = ref.loss_and_grads(lat, noise, t, emb)
+    noisy = ref.noise_sched.add_noise(lat, noise, t)
+    loss = trainer.forward_backward(noisy, t, emb, noise)
+    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < 1e-2
+    g, g_ref = trainer.flat_g, _flat(ref, trainer, "grad")
+    assert rel(g, g_ref) < 6e-2, rel(g, g_ref)        # activations / gradients are rounded to bf16 between "kernels"
+    assert not trainer.arena.live                      # arena fully reclaimed
+
+
+def test_train_step_adamw_and_polynomial_lr(fake_kernels):
+    kw = dict(lr=1e-3, weight_decay=1e-2, num_training_steps=4)
+    unet, trainer, ref = _tiny(4, **kw)
+    p0 = trainer.flat_p.clone()
+    for step in range(3):
+        lat, noise, t, emb = _batch(2, 16, seed=30 + step)
+        trainer.train_step(lat, noise, t, emb)
+        ref.train_step(lat, noise, t, emb)
+        assert abs(trainer.current_lr() - ref.opt.param_groups[0]["lr"]) < 1e-12
+    upd, upd_ref = trainer.flat_p - p0, _flat(ref, trainer, "param") - p0
+    assert torch.dot(upd, upd_ref) / (upd.norm() * upd_ref.norm()) > 0.97
+    from audioldm_with_lora_b200.train import polynomial_lr
+    assert polynomial_lr(0, 1e-5, 100) == pytest.approx(1e-5)
+    assert polynomial_lr(100, 1e-5, 100) == pytest.approx(1e-7)
+    assert polynomial_lr(1000, 1e-5, 100) == pytest.approx(1e-7)
+
+
+# ----------------------------------------------------------------------------------------- N > 1: DDP over gloo
+def _ddp_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, str(ROOT))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    _install_fakes()
+    kw = dict(lr=1e-3, weight_decay=0.0)
+    unet, trainer, _ = _tiny(4, **kw)
+    lat, noise, t, emb = _batch(1, 16, seed=70 + rank)          # each rank its own micro-batch
+    trainer.train_step(lat, noise, t, emb)                       # forward/backward, all-reduce, AdamW with 1/world
+    torch.save({"p": trainer.flat_p.clone(), "g": trainer.flat_g.clone()}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_ddp_step_matches_oracle_gradient_average(tmp_path, fake_kernels):
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_ddp_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = torch.load(tmp_path / "r0.pt"), torch.load(tmp_path / "r1.pt")
+    assert torch.equal(r0["g"], r1["g"]) and torch.equal(r0["p"], r1["p"])       # replicas stay in lock-step
+    kw = dict(lr=1e-3, weight_decay=0.0)
+    _, trainer, ref0 = _tiny(4, **kw)
+    _, _, ref1 = _tiny(4, **kw)
+    for rk, ref in enumerate((ref0, ref1)):
+        ref.loss_and_grads(*_batch(1, 16, seed=70 + rk))
+    ref0.average_grads_with([ref1])
+    g_mean = _flat(ref0, trainer, "grad")
+    assert rel(r0["g"] / world, g_mean) < 6e-2                   # the arena holds the SUM; AdamW applies 1/world
+    p0 = trainer.flat_p.clone()
+    ref0.optimizer_step()
+    upd, upd_ref = r0["p"] - p0, _flat(ref0, trainer, "param") - p0
+    assert torch.dot(upd, upd_ref) / (upd.norm() * upd_ref.norm()) > 0.97
