@@ -37,6 +37,9 @@
 #ifndef B200_GEMM_PROFILE
 #define B200_GEMM_PROFILE 0      // 1: CTA-0 cycle timeline + MMA-thread cost breakdown (B200_GEMM_DEBUG & 4 / & 8)
 #endif
+#ifndef B200_B_EARLY
+#define B200_B_EARLY 1           // 1: the weight producer does not wait for the previous grid (see the PDL note in the kernel)
+#endif
 #ifndef B200_SPLIT_PRODUCERS
 #define B200_SPLIT_PRODUCERS 1   // 1: activation (A) and weight (B) TMA streams issued by two different warps
 #endif
@@ -170,9 +173,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) TL(1);
-  // PDL: everything above overlapped the previous kernel's tail; from here on we touch its outputs.
+  // PDL: everything above overlapped the previous kernel's tail; from here on we touch its outputs -- except the
+  // weight (B) producer: weights are never written inside a step, so with split producers its TMA stream starts
+  // before the previous grid has drained (hides the HBM latency of the first weight tiles; B200_B_EARLY=0 disables).
   pdl_launch_dependents();
-  pdl_wait();
+  if (!(B200_SPLIT_PRODUCERS && B200_B_EARLY && warp == kProducerBWarp)) pdl_wait();
   if (threadIdx.x == 0) TL(2);
 
   if (warp == 0 || (B200_SPLIT_PRODUCERS && warp == kProducerBWarp)) {

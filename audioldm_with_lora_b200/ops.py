@@ -93,8 +93,10 @@ def _kb_cycles(bn: int, pair: bool = False) -> float:
     return max(2.0 * bn, (16384 + bn * (64 if pair else 128)) / 55.0)
 
 
-def choose_tiling(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_split: bool = True) -> Tuple[int, int]:
-    """(block_n, ksplit) minimising a wave/cycle model on 148 SMs; split-K only when it wins by > 25 %."""
+def choose_tiling(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_split: bool = True,
+                  num_sms: int = NUM_SMS) -> Tuple[int, int]:
+    """(block_n, ksplit) minimising a wave/cycle model on `num_sms` SMs (148, or this chain's share of them when
+    several sub-batch chains run concurrently); split-K only when it wins by > 25 %."""
     step = 128 if geglu else 64
     best = {}
     for ks in (1, 2, 3, 4):
@@ -103,9 +105,9 @@ def choose_tiling(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_
         for bn in range(step, 257, step):
             pair = CTA_PAIR and bn % 128 == 0 and m_tiles >= 2 and num_kb >= 16
             tiles1 = (2 * math.ceil(m_tiles / 2) if pair else m_tiles) * math.ceil(n / bn)
-            if ks > 1 and tiles1 > NUM_SMS // 2:
+            if ks > 1 and tiles1 > num_sms // 2:
                 continue
-            waves = math.ceil(tiles1 * ks / NUM_SMS)
+            waves = math.ceil(tiles1 * ks / num_sms)
             cost = waves * (math.ceil(num_kb / ks) * _kb_cycles(bn, pair) + 2 * bn) + 4000 + (7000 if ks > 1 else 0)
             key = 1 if ks == 1 else 2
             if key not in best or cost < best[key][0] - 1e-9:

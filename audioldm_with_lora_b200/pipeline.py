@@ -59,8 +59,8 @@ class _LoopState:
 
     def one_step(self, eng, guidance: float, overrides=None, branches: int = 1) -> None:
         eng.embed(self.t_steps, self.step, False, self.labels, None, self.silu_emb)
-        eng.forward_branched(self.xin, self.silu_emb, self.nb_unet, self.h, self.w, self.eps, branches=branches,
-                             attn_overrides=overrides)
+        eng.forward_nhwc(self.xin, self.silu_emb, self.nb_unet, self.h, self.w, self.eps, attn_overrides=overrides,
+                         mid_branches=branches)
         ops.sampler_step(self.eps, self.x, self.x_saved, self.hist, self.table, self.step, guidance, self.do_cfg,
                          self.nb_lat, self.h * self.w, eng.cfg.in_channels, LATENT_C_PAD, self.xin)
 
@@ -201,7 +201,10 @@ class AudioLDMPipeline:
         guidance = float(guidance_scale)
         overrides = self.unet.custom_attn_processors()
         branches = 1 if overrides else eng.effective_branches(st.nb_unet, self.branches)
-        eng._plan(st.nb_unet // branches, h, w)          # make sure weights are packed before the graph key is taken
+        eng._plan(st.nb_unet, h, w)          # make sure weights are packed before the graph key is taken
+        if branches > 1:
+            from .ops import NUM_SMS
+            eng._plan(st.nb_unet // branches, h, w, max(1, NUM_SMS // branches))
         graph_key = (guidance, eng.weights_version, eng.arena_token(st.nb_unet, h, w, branches), branches,
                      tuple(sorted(overrides or ())))
         if self.use_cuda_graph and (st.graph is None or st.graph_key != graph_key):

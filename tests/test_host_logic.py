@@ -339,3 +339,35 @@ def test_pipeline_call_contract(fake_kernels, tiny_weights):
     assert tuple(lat.shape) == (4, 8, 16, 16)
     # default length = sample_size * 4 * 0.01 s = 5.12 s -> latent height 128
     assert level_sizes(128)[3] == (16, 2)
+
+
+def test_branched_middle_region_equals_single_chain(fake_kernels):
+    """engine.forward_nhwc(mid_branches=k): the deep levels run as k sub-batch chains (parallel streams on the GPU,
+    sequential here) -- same result as the single chain, no arena leak, region boundaries as documented."""
+    import audioldm_with_lora_b200 as b2
+    from audioldm_with_lora_b200 import synthetic
+    from audioldm_with_lora_b200.arch import UNetConfig
+    from audioldm_with_lora_b200.engine import LATENT_C_PAD
+    tiny = UNetConfig("tiny", (64, 128, 192, 256))
+    unet = b2.UNet2DConditionModel(tiny, synthetic.random_unet_state_dict(tiny, seed=0), device="cpu")
+    unet.load_state_dict(synthetic.random_lora_state_dict(tiny, 4, fmt="peft"), strict=False)
+    eng = unet.engine
+    prog = eng.program()
+    i0, i1, need = eng.middle_region()
+    assert prog[i0][0] == "down" and prog[i0][2] == 1 and prog[i1 - 1][0] == "up" and prog[i1 - 1][2] == 2 and need == 0
+    assert all(st[2] >= 2 for st in prog[i0:i1] if st[0] in ("res", "tfm"))
+    assert all(st[2] < 2 for st in prog[:i0] + prog[i1:] if st[0] in ("res", "tfm"))
+    nb, h, w = 4, 24, 16
+    xin = torch.zeros(nb, h * w, LATENT_C_PAD, dtype=torch.bfloat16)
+    xin[:, :, :8] = torch.randn(nb, h * w, 8, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16)
+    silu = torch.randn(nb, tiny.temb_channels, generator=torch.Generator().manual_seed(4)).to(torch.bfloat16)
+    outs = []
+    for k in (1, 2, 4, 3):                       # 3 does not divide 4 -> falls back to 2
+        eps = torch.zeros(nb, h * w, 8)
+        eng.forward_nhwc(xin, silu, nb, h, w, eps, mid_branches=k)
+        assert not eng.arena.live
+        outs.append(eps)
+    for o in outs[1:]:
+        # not bit-equal: a different batch size changes the fp32 summation order inside the matmuls, and the
+        # bf16 roundings between layers amplify it to the usual bf16 noise floor (a logic error would be O(1))
+        assert ((o - outs[0]).norm() / outs[0].norm()).item() < 2e-2
