@@ -29,6 +29,7 @@ _PROTOS = {
     "b200_version": (c_int, []),
     "b200_last_error": (c_char_p, []),
     "b200_debug_timeline": (c_int, [c_void_p, c_int]),
+    "b200_set_sm_budget": (c_int, [c_int]),
     "b200_conv_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),

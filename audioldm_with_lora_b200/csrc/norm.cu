@@ -258,6 +258,15 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int M, int C, const float*
 
 using namespace b200;
 
+// SM share of the calling chain (0 = the whole GPU).  When several independent sub-batch chains run concurrently on
+// parallel streams, a GroupNorm launch sized for all 148 SMs (8-CTA clusters x images x group splits) serialises the
+// chains (measured: tools/concurrency_probe2.py); the host sets the budget around a chain's launches.
+static thread_local int g_sm_budget = 0;
+extern "C" int b200_set_sm_budget(int n) {
+  g_sm_budget = n > 0 ? n : 0;
+  return B200_OK;
+}
+
 static int groupnorm_impl(const void* x0, int c0, const void* x1, int c1, int nb, int hw, int groups, const float* gamma,
                           const float* beta, float eps, int silu, void* y, float* stats, void* stream_v);
 
@@ -292,10 +301,11 @@ static int groupnorm_impl(const void* x0, int c0, const void* x1, int c1, int nb
   // groups), the combination with the most CTAs whose clusters are all co-resident (one wave).
   static int max_active[4] = {-1, -1, -1, -1};      // for cs = 1, 2, 4, 8
   static const int max_cs = getenv("B200_GN_CLUSTER") ? atoi(getenv("B200_GN_CLUSTER")) : 8;   // debugging knob
+  static const int min_pix = getenv("B200_GN_MINPIX") ? atoi(getenv("B200_GN_MINPIX")) : 4;
   int best_cs = 1, best_gs = 1, best_ctas = 0;
   for (int ci = 3; ci >= 0; --ci) {
     const int cs = 1 << ci;
-    if (cs > max_cs || (cs > 1 && hw < 4 * cs)) continue;
+    if (cs > max_cs || (cs > 1 && hw < min_pix * cs)) continue;     // a slab of fewer pixels per CTA is all sync, no work
     if (max_active[ci] < 0) {
       cudaLaunchConfig_t qc;
       memset(&qc, 0, sizeof(qc));
@@ -317,6 +327,7 @@ static int groupnorm_impl(const void* x0, int c0, const void* x1, int c1, int nb
       if (groups % gs != 0 || (C / gs) % 8 != 0) continue;
       if (nb * gs > max_active[ci]) continue;
       const int ctas = nb * gs * cs;
+      if (g_sm_budget > 0 && ctas > g_sm_budget && ctas > nb) continue;
       if (ctas > best_ctas) {                        // ties keep the larger cluster / smaller split seen first
         best_ctas = ctas; best_cs = cs; best_gs = gs;
       }

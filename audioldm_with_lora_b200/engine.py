@@ -414,8 +414,12 @@ class UNetEngine:
             r = _Runner(self, sub, h, w, arenas[b], None, None, None, rowvec=main.rowvec[b * sub:(b + 1) * sub],
                         sms=share)
             sk = [(t[b * rows_in:(b + 1) * rows_in], c) for t, c in outer]
-            r.run(prog[i0:i1], hcur[b * rows_in:(b + 1) * rows_in], sk,
-                  final_out=region_out[b * rows_out:(b + 1) * rows_out])
+            ops.set_sm_budget(share)
+            try:
+                r.run(prog[i0:i1], hcur[b * rows_in:(b + 1) * rows_in], sk,
+                      final_out=region_out[b * rows_out:(b + 1) * rows_out])
+            finally:
+                ops.set_sm_budget(0)
             r.finish(keep_rowvec=True)
 
         if self.device.type != "cuda":          # host-logic tests (tests/fake_ops.py): same split, no streams

@@ -150,6 +150,11 @@ def conv_gemm(pw: PackedWeight, a0: Tensor, nb: int, h: int, w: int, out: Tensor
     return out
 
 
+def set_sm_budget(n: int) -> None:
+    """Launch-shape hint for the following launches of this thread (0 = the whole GPU); see b200_set_sm_budget."""
+    _lib.check(_lib.load().b200_set_sm_budget(int(n)), "b200_set_sm_budget")
+
+
 def groupnorm_silu(x0: Tensor, c0: int, x1: Optional[Tensor], c1: int, nb: int, hw: int, gamma: Tensor, beta: Tensor,
                    eps: float, silu: bool, y: Tensor, groups: int = 32) -> Tensor:
     assert x0.dtype == torch.bfloat16 and y.dtype == torch.bfloat16

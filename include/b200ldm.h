@@ -54,6 +54,10 @@ int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, const void* a
                    int out_fp32, int geglu, int block_n, int max_ctas, int ksplit, float* workspace, int cta_pair,
                    void* stream);
 
+/* Launch-shape hint for the calling thread: the number of SMs the following launches should size themselves for
+ * (0 = all).  Used when independent sub-batch chains run concurrently on parallel streams. */
+int b200_set_sm_budget(int n);
+
 /* GroupNorm (+ optional SiLU) over one or two NHWC sources (cat along C is never materialised).
  * One launch: a thread-block cluster per image exchanges the group statistics through DSMEM.
  * Replaces F.group_norm + F.silu in ResnetBlock2D / Transformer2DModel.norm / conv_norm_out

@@ -54,6 +54,10 @@ def conv_gemm(pw, a0, nb, h, w, out, *, a1=None, a2=None, stride=1, rowvec=None,
     return out
 
 
+def set_sm_budget(n):
+    pass
+
+
 def groupnorm_silu(x0, c0, x1, c1, nb, hw, gamma, beta, eps, silu, y, groups=32):
     x = x0.view(nb, hw, c0).float()
     if c1:
@@ -326,5 +330,5 @@ def install(monkeypatch, ops_module):
     """Replace the kernel wrappers of `ops_module` (keeps PackedWeight / tiling helpers)."""
     for name in ("conv_gemm", "groupnorm_silu", "layernorm", "attention", "time_class_embed",
                  "pack_nchw_to_nhwc", "unpack_nhwc_to_nchw", "upsample_nearest", "sampler_step", "add_noise",
-                 "adamw_flat", "mse_partial") + TRAIN_OPS:
+                 "adamw_flat", "mse_partial", "set_sm_budget") + TRAIN_OPS:
         monkeypatch.setattr(ops_module, name, globals()[name])
