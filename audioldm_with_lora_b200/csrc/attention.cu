@@ -29,9 +29,11 @@
 namespace b200 {
 
 static constexpr int kQ = 128;                 // query rows per CTA
-static constexpr int kKV = 128;                // keys per block
 static constexpr int kAttnThreads = 192;       // warps 0-3 softmax, warp 4 TMA, warp 5 MMA
-static constexpr int kOnesBytes = 4096;        // 16 columns of bf16 1.0 behind every V tile (MN-major: 2 chunks x 2048 B)
+// Keys per block: template parameter KV (128, or 64 for small head_dim: S (64 columns) + O (d + 16) then fit 128 TMEM
+// columns and ~44 KB of shared memory, so FOUR CTAs share an SM instead of two and hide each other's
+// MMA -> softmax -> MMA hand-offs; the kernel is bound by those hand-offs, not by any pipe).
+// Behind every V tile: 16 columns of bf16 1.0 (MN-major: 2 chunks of KV x 16 B).
 static constexpr float kRescaleThreshold = 8.0f;   // move the reference maximum when a row maximum exceeds it by 2^8
 
 struct AttnParams {
@@ -62,12 +64,12 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
   return y;
 }
 
-// max over one 128-column S row in TMEM (two 32-column loads in flight at a time)
-template <bool kMasked>
+// max over one KV-column S row in TMEM (two 32-column loads in flight at a time)
+template <bool kMasked, int KV>
 __device__ __forceinline__ float row_max(uint32_t t_row, int kvalid) {
   float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-  for (int c = 0; c < 4; c += 2) {
+  for (int c = 0; c < KV / 32; c += 2) {
     uint32_t r0[32], r1[32];
     tmem_ld_x32(t_row + c * 32, r0);
     tmem_ld_x32(t_row + (c + 1) * 32, r1);
@@ -88,18 +90,18 @@ __device__ __forceinline__ float row_max(uint32_t t_row, int kvalid) {
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-// One pass over a 128-column S row: p = exp2(s * scale - ref) as bf16 into the K-major core-matrix smem tile.
+// One pass over a KV-column S row: p = exp2(s * scale - ref) as bf16 into the K-major core-matrix smem tile.
 // Returns max_j (s_j * scale - ref) (bf16 precision: it only feeds the rescale decision).
 // The next 32-column TMEM load is issued before the current one is processed.
-template <bool kMasked, bool kPackedExp>
+template <bool kMasked, bool kPackedExp, int KV>
 __device__ __forceinline__ float exp_store(uint32_t t_row, uint8_t* sp_row, float scale_log2, float neg_ref, int kvalid) {
   uint32_t mx = 0xFF80FF80u;                      // (-inf, -inf) in bf16x2
   uint32_t r[2][32];
   tmem_ld_x32(t_row, r[0]);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < KV / 32; ++c) {
     tmem_wait_ld();
-    if (c + 1 < 4) tmem_ld_x32(t_row + (c + 1) * 32, r[(c + 1) & 1]);
+    if (c + 1 < KV / 32) tmem_ld_x32(t_row + (c + 1) * 32, r[(c + 1) & 1]);
     const uint32_t(&cur)[32] = r[c & 1];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -136,14 +138,18 @@ __device__ __forceinline__ void scale_o(uint32_t t_o_row, int ncols, float f) {
   tmem_wait_st();
 }
 
-template <int D>
+template <int D, int KV>
 __global__ void __launch_bounds__(kAttnThreads)
-attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  constexpr int kTileBytes = 128 * D * 2;       // one Q / K / V tile
+  constexpr int kKV = KV;
+  constexpr int kTileBytes = 128 * D * 2;       // the Q tile
+  constexpr int kKVTile = KV * D * 2;           // one K / V tile
+  constexpr int kChunk = KV * 16;               // bytes between 8-element chunks of a K / V tile
+  constexpr int kOnesBytes = 2 * kChunk;
   constexpr int kPBytes = kQ * kKV * 2;
-  constexpr int kStageBytes = 2 * kTileBytes + kOnesBytes;      // K tile, V tile, ones columns
+  constexpr int kStageBytes = 2 * kKVTile + kOnesBytes;         // K tile, V tile, ones columns
   constexpr int kOCols = D + 16;                // O accumulator columns: d outputs + the denominator (x16)
   uint8_t* sQ = smem;
   uint8_t* sP = sQ + kTileBytes;
@@ -183,7 +189,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
   // the ones columns behind every V tile (never overwritten: the TMA box covers the V tile only)
   for (int i = threadIdx.x; i < p.stages * (kOnesBytes / 16); i += kAttnThreads) {
     const int st = i / (kOnesBytes / 16), off = i % (kOnesBytes / 16);
-    *reinterpret_cast<uint4*>(sKV + st * kStageBytes + 2 * kTileBytes + off * 16) =
+    *reinterpret_cast<uint4*>(sKV + st * kStageBytes + 2 * kKVTile + off * 16) =
         make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   }
   fence_proxy_async_smem();
@@ -197,8 +203,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();
-  const uint32_t t_s = tmem_base;               // S: columns [0, 128)
-  const uint32_t t_o = tmem_base + 128;         // O: columns [128, 128 + D + 16)
+  const uint32_t t_s = tmem_base;               // S: columns [0, KV)
+  const uint32_t t_o = tmem_base + KV;          // O: columns [KV, KV + D + 16)
 
   if (warp == 4) {
     // ============================================================ TMA producer
@@ -210,9 +216,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
       for (int j = 0; j < p.nblk; ++j) {
         mbar_wait(&kv_empty[s], ph ^ 1);
         uint8_t* k_dst = sKV + s * kStageBytes;
-        mbar_expect_tx(&kv_full[s], 2 * kTileBytes);
-        tma_load_4d(k_dst, &tmQKV, &kv_full[s], 0, j * kKV, chunk_k, b);
-        tma_load_4d(k_dst + kTileBytes, &tmQKV, &kv_full[s], 0, j * kKV, chunk_v, b);
+        mbar_expect_tx(&kv_full[s], 2 * kKVTile);
+        tma_load_4d(k_dst, &tmKV, &kv_full[s], 0, j * kKV, chunk_k, b);
+        tma_load_4d(k_dst + kKVTile, &tmKV, &kv_full[s], 0, j * kKV, chunk_v, b);
         if (++s == p.stages) {
           s = 0;
           ph ^= 1;
@@ -222,13 +228,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
   } else if (warp == 5) {
     // ============================================================ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_s = make_idesc_bf16(128, KV, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(128, kOCols, 0, 1);  // B = [V | 1], MN-major
       // no-swizzle canonical layouts: core matrix = 8 rows x 16 B, contiguous (128 B).
-      //  K-major tile [128 rows][D]: next 8-row group +128 B (SBO), next 8-elem K chunk +2048 B (LBO)
-      //  MN-major V   [128 keys][D]: next 8-key group +128 B (LBO), next 8-elem d chunk +2048 B (SBO)
-      const uint32_t k_lbo = (p.variant & 1) ? 128 : 2048, k_sbo = (p.variant & 1) ? 2048 : 128;
-      const uint32_t v_lbo = (p.variant & 2) ? 2048 : 128, v_sbo = (p.variant & 2) ? 128 : 2048;
+      //  K-major tile [R rows][D]: next 8-row group +128 B (SBO), next 8-elem K chunk +R*16 B (LBO); R = 128 (Q, P) or KV (K)
+      //  MN-major V   [KV keys][D]: next 8-key group +128 B (LBO), next 8-elem d chunk +KV*16 B (SBO)
+      const uint32_t q_lbo = (p.variant & 1) ? 128 : 2048, q_sbo = (p.variant & 1) ? 2048 : 128;
+      const uint32_t k_lbo = (p.variant & 1) ? 128 : kChunk, k_sbo = (p.variant & 1) ? kChunk : 128;
+      const uint32_t v_lbo = (p.variant & 2) ? kChunk : 128, v_sbo = (p.variant & 2) ? 128 : kChunk;
       const uint32_t q_addr = smem_u32(sQ);
       const uint32_t p_addr = smem_u32(sP);
       mbar_wait(q_full, 0);
@@ -236,14 +243,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
       uint32_t ph = 0;
       for (int j = 0; j < p.nblk; ++j) {
         const uint32_t k_addr = smem_u32(sKV + s * kStageBytes);
-        const uint32_t v_addr = k_addr + kTileBytes;
+        const uint32_t v_addr = k_addr + kKVTile;
         mbar_wait(&kv_full[s], ph);
         tc_fence_after();
         // S = Q K^T   (the previous block's softmax finished reading S before it released p_full)
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
-          const uint64_t a_desc = make_smem_desc(q_addr + k * 4096, k_lbo, k_sbo, SWZ_NONE);
-          const uint64_t b_desc = make_smem_desc(k_addr + k * 4096, k_lbo, k_sbo, SWZ_NONE);
+          const uint64_t a_desc = make_smem_desc(q_addr + k * 4096, q_lbo, q_sbo, SWZ_NONE);
+          const uint64_t b_desc = make_smem_desc(k_addr + k * 2 * kChunk, k_lbo, k_sbo, SWZ_NONE);
           umma_bf16_ss(t_s, a_desc, b_desc, idesc_s, k != 0);
         }
         umma_commit(s_full);
@@ -252,7 +259,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < kKV / 16; ++k) {
-          const uint64_t a_desc = make_smem_desc(p_addr + k * 4096, k_lbo, k_sbo, SWZ_NONE);
+          const uint64_t a_desc = make_smem_desc(p_addr + k * 4096, q_lbo, q_sbo, SWZ_NONE);
           const uint64_t b_desc = make_smem_desc(v_addr + k * 256, v_lbo, v_sbo, SWZ_NONE);
           umma_bf16_ss(t_o, a_desc, b_desc, idesc_o, (j | k) != 0);
         }
@@ -277,7 +284,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       if (j == 0) {
-        const float mx = full ? row_max<false>(t_s + lane_off, kvalid) : row_max<true>(t_s + lane_off, kvalid);
+        const float mx = full ? row_max<false, KV>(t_s + lane_off, kvalid) : row_max<true, KV>(t_s + lane_off, kvalid);
         ref = mx * p.scale_log2;
       } else {
         // sP is free again (and O is quiescent) once the previous block's P V has completed
@@ -285,22 +292,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
         tc_fence_after();
       }
       float over;
-      if (packed) over = full ? exp_store<false, true>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
-                              : exp_store<true, true>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid);
-      else over = full ? exp_store<false, false>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
-                       : exp_store<true, false>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid);
+      if (packed) over = full ? exp_store<false, true, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
+                              : exp_store<true, true, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid);
+      else over = full ? exp_store<false, false, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
+                       : exp_store<true, false, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid);
       // warp-uniform decision (the TMEM loads / stores below are warp-collective)
       if (__any_sync(0xffffffffu, over > kRescaleThreshold)) {
         // rare: a row's maximum moved by more than 2^8 -> every row of the warp takes its current maximum as the
         // new reference, O (with its denominator column) is rescaled, and the block's probabilities are redone
-        const float mx = full ? row_max<false>(t_s + lane_off, kvalid) : row_max<true>(t_s + lane_off, kvalid);
+        const float mx = full ? row_max<false, KV>(t_s + lane_off, kvalid) : row_max<true, KV>(t_s + lane_off, kvalid);
         const float new_ref = fmaxf(ref, mx * p.scale_log2);
         scale_o(t_o + lane_off, kOCols, ex2_approx(ref - new_ref));
         ref = new_ref;
-        if (packed) (void)(full ? exp_store<false, true>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
-                                : exp_store<true, true>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid));
-        else (void)(full ? exp_store<false, false>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
-                         : exp_store<true, false>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid));
+        if (packed) (void)(full ? exp_store<false, true, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
+                                : exp_store<true, true, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid));
+        else (void)(full ? exp_store<false, false, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
+                         : exp_store<true, false, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid));
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -344,23 +351,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) 
   }
 }
 
-template <int D>
-static int launch_attention(const CUtensorMap& tm, AttnParams& p, cudaStream_t stream) {
+template <int D, int KV>
+static int launch_attention(const CUtensorMap& tm, const CUtensorMap& tmkv, AttnParams& p, cudaStream_t stream) {
   constexpr int kTileBytes = 128 * D * 2;
-  constexpr int kStageBytes = 2 * kTileBytes + kOnesBytes;
-  const int fixed = kTileBytes + kQ * kKV * 2 + 128 /*barriers*/ + 128 /*align*/;
-  // two resident CTAs per SM when TMEM allows (256 columns each)
-  const int budget = (p.tmem_cols <= 256) ? 110 * 1024 : 220 * 1024;
+  constexpr int kStageBytes = 2 * KV * D * 2 + 2 * KV * 16;
+  const int fixed = kTileBytes + kQ * KV * 2 + 128 /*barriers*/ + 128 /*align*/;
+  // resident CTAs per SM are set by TMEM: 512 / tmem_cols (4, 2 or 1); give each its share of shared memory
+  const int per_sm = 512 / p.tmem_cols;
+  const int budget = (220 * 1024) / per_sm;
   p.stages = (fixed + 2 * kStageBytes <= budget) ? 2 : 1;
   const int smem_bytes = fixed + p.stages * kStageBytes;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<D, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(B200_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
   dim3 grid((p.seq + kQ - 1) / kQ, p.batch * p.heads);
-  B200_CHECK_PDL("attention", launch_pdl(attention_kernel<D>, grid, dim3(kAttnThreads), (size_t)smem_bytes, stream, 0, tm, p));
+  B200_CHECK_PDL("attention", launch_pdl(attention_kernel<D, KV>, grid, dim3(kAttnThreads), (size_t)smem_bytes, stream, 0, tm,
+                                         tmkv, p));
   return B200_OK;
 }
 
@@ -391,30 +400,34 @@ static int attention_impl(const void* qkv, void* out, float* lse, int batch, int
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.seq = seq; p.heads = heads; p.d = head_dim; p.batch = batch;
-  p.nblk = (seq + kKV - 1) / kKV;
-  p.tmem_cols = (head_dim + 16 <= 128) ? 256 : 512;
+  static const int kv_env = getenv("B200_ATTN_KV") ? atoi(getenv("B200_ATTN_KV")) : 0;     // A/B knob: 64 or 128
+  const int kv = (head_dim <= 48 && kv_env != 128) ? 64 : 128;
+  p.nblk = (seq + kv - 1) / kv;
+  int cols = 32;
+  while (cols < kv + head_dim + 16) cols *= 2;
+  p.tmem_cols = cols;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.out_ld = C;
   p.variant = variant;
   p.lse = lse;
 
-  CUtensorMap tm;
-  {
-    // dims (innermost first): 8 elems | seq rows | 16-byte chunks across [Q|K|V] | batch
+  CUtensorMap tm, tmkv;
+  for (int which = 0; which < 2; ++which) {
+    // dims (innermost first): 8 elems | seq rows | 16-byte chunks across [Q|K|V] | batch; box rows: 128 (Q) or kv (K, V)
     uint64_t dims[4] = {8, (uint64_t)seq, (uint64_t)(3 * C / 8), (uint64_t)batch};
     uint64_t strides[3] = {(uint64_t)3 * C, 8, (uint64_t)seq * 3 * C};
-    uint32_t box[4] = {8, 128, (uint32_t)(head_dim / 8), 1};
-    int rc = make_tmap_bf16(&tm, qkv, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    uint32_t box[4] = {8, (uint32_t)(which ? kv : 128), (uint32_t)(head_dim / 8), 1};
+    int rc = make_tmap_bf16(which ? &tmkv : &tm, qkv, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
   }
   switch (head_dim) {
-    case 32: return launch_attention<32>(tm, p, stream);
-    case 48: return launch_attention<48>(tm, p, stream);
-    case 64: return launch_attention<64>(tm, p, stream);
-    case 80: return launch_attention<80>(tm, p, stream);
-    case 96: return launch_attention<96>(tm, p, stream);
-    case 160: return launch_attention<160>(tm, p, stream);
+    case 32: return kv == 64 ? launch_attention<32, 64>(tm, tmkv, p, stream) : launch_attention<32, 128>(tm, tmkv, p, stream);
+    case 48: return kv == 64 ? launch_attention<48, 64>(tm, tmkv, p, stream) : launch_attention<48, 128>(tm, tmkv, p, stream);
+    case 64: return launch_attention<64, 128>(tm, tmkv, p, stream);
+    case 80: return launch_attention<80, 128>(tm, tmkv, p, stream);
+    case 96: return launch_attention<96, 128>(tm, tmkv, p, stream);
+    case 160: return launch_attention<160, 128>(tm, tmkv, p, stream);
     default: return fail(B200_ERR_UNSUPPORTED, "attention: head_dim %d unsupported (32/48/64/80/96/160)", head_dim);
   }
 }

@@ -26,13 +26,17 @@
 
 namespace b200 {
 
-static constexpr int kBT = 128;                // rows per CTA and columns per streamed block
+static constexpr int kBT = 128;                // rows per CTA
 static constexpr int kBwdThreads = 192;        // warps 0-3 elementwise, warp 4 TMA, warp 5 MMA
+// Columns per streamed block: template parameter BC (128, or 64 for head_dim <= 48: two 64-column score tiles + two
+// accumulators then fit 256 TMEM columns and ~64 KB of shared memory, so two CTAs share an SM and overlap each other's
+// MMA -> elementwise -> MMA hand-offs).
 
 struct AttnBwdParams {
   int seq, heads, batch;
-  int nblk;                 // ceil(seq / 128)
+  int nblk;                 // ceil(seq / BC)
   int stages;
+  int tmem_cols;
   float scale_log2;         // scale * log2(e)
   float scale;
   const float* lse;         // [batch, heads, seq] (log2 domain)
@@ -47,20 +51,23 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-template <int D, bool kModeQ>
+template <int D, int BC, bool kModeQ>
 __global__ void __launch_bounds__(kBwdThreads)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                     const __grid_constant__ CUtensorMap tmQKVc, const __grid_constant__ CUtensorMap tmDOc,
                      const AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  constexpr int kTileBytes = 128 * D * 2;
-  constexpr int kPBytes = kBT * kBT * 2;
+  constexpr int kTileBytes = 128 * D * 2;       // resident X tiles (box of 128 rows: maps tmQKV / tmDO)
+  constexpr int kYTile = BC * D * 2;            // streamed Y tiles (box of BC rows: maps tmQKVc / tmDOc)
+  constexpr int kChunkY = BC * 16;              // bytes between 8-element chunks of a Y tile
+  constexpr int kPBytes = kBT * BC * 2;
   uint8_t* sX1 = smem;
   uint8_t* sX2 = sX1 + kTileBytes;
   uint8_t* sP = sX2 + kTileBytes;               // P^T (mode KV only)
   uint8_t* sDS = sP + kPBytes;                  // dS^T / dS
   uint8_t* sY = sDS + kPBytes;                  // stages x {Y1, Y2}
-  float* s_stat = reinterpret_cast<float*>(sY + p.stages * 2 * kTileBytes);     // [2][128]: lse, delta of the column block
+  float* s_stat = reinterpret_cast<float*>(sY + p.stages * 2 * kYTile);         // [2][128]: lse, delta of the column block
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 256);
   uint64_t* x_full = bars;
   uint64_t* y_full = bars + 1;                  // [2]
@@ -84,6 +91,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmQKVc);
+    tma_prefetch_desc(&tmDOc);
     mbar_init(x_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&y_full[i], 1);
@@ -95,7 +104,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     fence_barrier_init();
   }
   if (warp == 4) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -104,10 +113,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();
-  const uint32_t t_1 = tmem_base;               // T1: columns [0, 128)
-  const uint32_t t_2 = tmem_base + 128;         // T2: columns [128, 256)
-  const uint32_t t_a1 = tmem_base + 256;        // Acc1 (dV): [256, 256 + D)
-  const uint32_t t_a2 = tmem_base + 256 + D;    // Acc2 (dK or dQ): [256 + D, 256 + 2D)
+  const uint32_t t_1 = tmem_base;                   // T1: columns [0, BC)
+  const uint32_t t_2 = tmem_base + BC;              // T2: columns [BC, 2 BC)
+  const uint32_t t_a1 = tmem_base + 2 * BC;         // Acc1 (dV): [2 BC, 2 BC + D)
+  const uint32_t t_a2 = tmem_base + 2 * BC + D;     // Acc2 (dK or dQ): [2 BC + D, 2 BC + 2 D)
 
   if (warp == 4) {
     // ============================================================ TMA producer
@@ -124,14 +133,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       uint32_t ph = 0;
       for (int j = 0; j < p.nblk; ++j) {
         mbar_wait(&y_empty[s], ph ^ 1);
-        uint8_t* dst = sY + s * 2 * kTileBytes;
-        mbar_expect_tx(&y_full[s], 2 * kTileBytes);
+        uint8_t* dst = sY + s * 2 * kYTile;
+        mbar_expect_tx(&y_full[s], 2 * kYTile);
         if (kModeQ) {
-          tma_load_4d(dst, &tmQKV, &y_full[s], 0, j * kBT, chunk_k, b);
-          tma_load_4d(dst + kTileBytes, &tmQKV, &y_full[s], 0, j * kBT, chunk_v, b);
+          tma_load_4d(dst, &tmQKVc, &y_full[s], 0, j * BC, chunk_k, b);
+          tma_load_4d(dst + kYTile, &tmQKVc, &y_full[s], 0, j * BC, chunk_v, b);
         } else {
-          tma_load_4d(dst, &tmQKV, &y_full[s], 0, j * kBT, chunk_q, b);
-          tma_load_4d(dst + kTileBytes, &tmDO, &y_full[s], 0, j * kBT, chunk_q, b);
+          tma_load_4d(dst, &tmQKVc, &y_full[s], 0, j * BC, chunk_q, b);
+          tma_load_4d(dst + kYTile, &tmDOc, &y_full[s], 0, j * BC, chunk_q, b);
         }
         if (++s == p.stages) {
           s = 0;
@@ -142,7 +151,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   } else if (warp == 5) {
     // ============================================================ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_t = make_idesc_bf16(128, 128, 0, 0);       // T = X Y^T, both K-major
+      const uint32_t idesc_t = make_idesc_bf16(128, BC, 0, 0);        // T = X Y^T, both K-major
       const uint32_t idesc_a = make_idesc_bf16(128, D, 0, 1);         // Acc += P Y, Y MN-major
       const uint32_t x1_addr = smem_u32(sX1), x2_addr = smem_u32(sX2);
       const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
@@ -150,20 +159,20 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < p.nblk; ++j) {
-        const uint32_t y1_addr = smem_u32(sY + s * 2 * kTileBytes);
-        const uint32_t y2_addr = y1_addr + kTileBytes;
+        const uint32_t y1_addr = smem_u32(sY + s * 2 * kYTile);
+        const uint32_t y2_addr = y1_addr + kYTile;
         mbar_wait(&y_full[s], ph);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint64_t a_desc = make_smem_desc(x1_addr + k * 4096, 2048, 128, SWZ_NONE);
-          const uint64_t b_desc = make_smem_desc(y1_addr + k * 4096, 2048, 128, SWZ_NONE);
+          const uint64_t b_desc = make_smem_desc(y1_addr + k * 2 * kChunkY, kChunkY, 128, SWZ_NONE);
           umma_bf16_ss(t_1, a_desc, b_desc, idesc_t, k != 0);
         }
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint64_t a_desc = make_smem_desc(x2_addr + k * 4096, 2048, 128, SWZ_NONE);
-          const uint64_t b_desc = make_smem_desc(y2_addr + k * 4096, 2048, 128, SWZ_NONE);
+          const uint64_t b_desc = make_smem_desc(y2_addr + k * 2 * kChunkY, kChunkY, 128, SWZ_NONE);
           umma_bf16_ss(t_2, a_desc, b_desc, idesc_t, k != 0);
         }
         umma_commit(t_full);
@@ -172,16 +181,16 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         tc_fence_after();
         if (!kModeQ) {
 #pragma unroll
-          for (int k = 0; k < kBT / 16; ++k) {
+          for (int k = 0; k < BC / 16; ++k) {
             const uint64_t a_desc = make_smem_desc(p_addr + k * 4096, 2048, 128, SWZ_NONE);
-            const uint64_t b_desc = make_smem_desc(y2_addr + k * 256, 128, 2048, SWZ_NONE);
+            const uint64_t b_desc = make_smem_desc(y2_addr + k * 256, 128, kChunkY, SWZ_NONE);
             umma_bf16_ss(t_a1, a_desc, b_desc, idesc_a, (j | k) != 0);
           }
         }
 #pragma unroll
-        for (int k = 0; k < kBT / 16; ++k) {
+        for (int k = 0; k < BC / 16; ++k) {
           const uint64_t a_desc = make_smem_desc(ds_addr + k * 4096, 2048, 128, SWZ_NONE);
-          const uint64_t b_desc = make_smem_desc(y1_addr + k * 256, 128, 2048, SWZ_NONE);
+          const uint64_t b_desc = make_smem_desc(y1_addr + k * 256, 128, kChunkY, SWZ_NONE);
           umma_bf16_ss(t_a2, a_desc, b_desc, idesc_a, (j | k) != 0);
         }
         umma_commit(&y_empty[s]);
@@ -205,20 +214,22 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       row_delta = p.delta[stat_base + r0 + row];
     }
     for (int j = 0; j < p.nblk; ++j) {
-      const int cvalid = min(kBT, p.seq - j * kBT);
+      const int cvalid = min(BC, p.seq - j * BC);
       if (!kModeQ) {
-        // statistics of this block's 128 columns (= queries); the previous block's readers are past ps_full
+        // statistics of this block's BC columns (= queries); the previous block's readers are past ps_full
         named_bar_sync(1, 128);
-        const int col = j * kBT + row;
-        s_stat[row] = col < p.seq ? p.lse[stat_base + col] : 0.f;
-        s_stat[128 + row] = col < p.seq ? p.delta[stat_base + col] : 0.f;
+        const int col = j * BC + row;
+        if (row < BC) {
+          s_stat[row] = col < p.seq ? p.lse[stat_base + col] : 0.f;
+          s_stat[128 + row] = col < p.seq ? p.delta[stat_base + col] : 0.f;
+        }
         named_bar_sync(1, 128);
       }
       // T1 / T2 of this block are complete; every earlier MMA (incl. the previous block's reads of sP / sDS) too
       mbar_wait(t_full, j & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < BC / 32; ++c) {
         uint32_t r1[32], r2[32];
         tmem_ld_x32(t_1 + lane_off + c * 32, r1);
         tmem_ld_x32(t_2 + lane_off + c * 32, r2);
@@ -286,7 +297,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -314,25 +325,32 @@ attention_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16*
   }
 }
 
-template <int D>
-static int launch_attention_bwd(const CUtensorMap& tq, const CUtensorMap& td, AttnBwdParams& p, cudaStream_t stream) {
+template <int D, int BC>
+static int launch_attention_bwd(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tqc, const CUtensorMap& tdc,
+                                AttnBwdParams& p, cudaStream_t stream) {
   constexpr int kTileBytes = 128 * D * 2;
-  const int fixed = 2 * kTileBytes + 2 * kBT * kBT * 2 + 1024 /*stats*/ + 128 /*barriers*/ + 128 /*align*/;
-  p.stages = (fixed + 2 * 2 * kTileBytes <= 220 * 1024) ? 2 : 1;
-  const int smem_bytes = fixed + p.stages * 2 * kTileBytes;
+  constexpr int kYTile = BC * D * 2;
+  const int fixed = 2 * kTileBytes + 2 * kBT * BC * 2 + 1024 /*stats*/ + 128 /*barriers*/ + 128 /*align*/;
+  int cols = 32;
+  while (cols < 2 * BC + 2 * D) cols *= 2;
+  p.tmem_cols = cols;
+  p.nblk = (p.seq + BC - 1) / BC;
+  const int budget = (220 * 1024) / (512 / cols);
+  p.stages = (fixed + 2 * 2 * kYTile <= budget) ? 2 : 1;
+  const int smem_bytes = fixed + p.stages * 2 * kYTile;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<D, BC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_bwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(attention_bwd_kernel<D, BC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(B200_ERR_CUDA, "attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
   dim3 grid((p.seq + kBT - 1) / kBT, p.batch * p.heads);
-  B200_CHECK_PDL("attention_bwd(kv)", launch_pdl(attention_bwd_kernel<D, false>, grid, dim3(kBwdThreads), (size_t)smem_bytes,
-                                                 stream, 0, tq, td, p));
-  B200_CHECK_PDL("attention_bwd(q)", launch_pdl(attention_bwd_kernel<D, true>, grid, dim3(kBwdThreads), (size_t)smem_bytes,
-                                                stream, 0, tq, td, p));
+  B200_CHECK_PDL("attention_bwd(kv)", launch_pdl(attention_bwd_kernel<D, BC, false>, grid, dim3(kBwdThreads), (size_t)smem_bytes,
+                                                 stream, 0, tq, td, tqc, tdc, p));
+  B200_CHECK_PDL("attention_bwd(q)", launch_pdl(attention_bwd_kernel<D, BC, true>, grid, dim3(kBwdThreads), (size_t)smem_bytes,
+                                                stream, 0, tq, td, tqc, tdc, p));
   return B200_OK;
 }
 
@@ -359,33 +377,37 @@ extern "C" int b200_attention_bwd(const void* qkv, const void* o, const void* do
   AttnBwdParams p;
   memset(&p, 0, sizeof(p));
   p.seq = seq; p.heads = heads; p.batch = batch;
-  p.nblk = (seq + kBT - 1) / kBT;
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse; p.delta = delta;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   p.ld = 3 * C;
-  CUtensorMap tq, td;
-  {
-    uint64_t dims[4] = {8, (uint64_t)seq, (uint64_t)(3 * C / 8), (uint64_t)batch};
-    uint64_t strides[3] = {(uint64_t)3 * C, 8, (uint64_t)seq * 3 * C};
-    uint32_t box[4] = {8, 128, (uint32_t)(head_dim / 8), 1};
-    int rc = make_tmap_bf16(&tq, qkv, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
-    if (rc) return rc;
-  }
-  {
-    uint64_t dims[4] = {8, (uint64_t)seq, (uint64_t)(C / 8), (uint64_t)batch};
-    uint64_t strides[3] = {(uint64_t)C, 8, (uint64_t)seq * C};
-    uint32_t box[4] = {8, 128, (uint32_t)(head_dim / 8), 1};
-    int rc = make_tmap_bf16(&td, dout, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
-    if (rc) return rc;
+  static const int bc_env = getenv("B200_ATTN_BWD_BC") ? atoi(getenv("B200_ATTN_BWD_BC")) : 0;     // A/B knob: 64 or 128
+  const int bc = (head_dim <= 48 && bc_env != 128) ? 64 : 128;
+  CUtensorMap tq, td, tqc, tdc;
+  for (int which = 0; which < 2; ++which) {
+    const uint32_t rows = which ? (uint32_t)bc : 128u;
+    {
+      uint64_t dims[4] = {8, (uint64_t)seq, (uint64_t)(3 * C / 8), (uint64_t)batch};
+      uint64_t strides[3] = {(uint64_t)3 * C, 8, (uint64_t)seq * 3 * C};
+      uint32_t box[4] = {8, rows, (uint32_t)(head_dim / 8), 1};
+      int rc = make_tmap_bf16(which ? &tqc : &tq, qkv, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+      if (rc) return rc;
+    }
+    {
+      uint64_t dims[4] = {8, (uint64_t)seq, (uint64_t)(C / 8), (uint64_t)batch};
+      uint64_t strides[3] = {(uint64_t)C, 8, (uint64_t)seq * C};
+      uint32_t box[4] = {8, rows, (uint32_t)(head_dim / 8), 1};
+      int rc = make_tmap_bf16(which ? &tdc : &td, dout, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+      if (rc) return rc;
+    }
   }
   switch (head_dim) {
-    case 32: return launch_attention_bwd<32>(tq, td, p, stream);
-    case 48: return launch_attention_bwd<48>(tq, td, p, stream);
-    case 64: return launch_attention_bwd<64>(tq, td, p, stream);
-    case 80: return launch_attention_bwd<80>(tq, td, p, stream);
-    case 96: return launch_attention_bwd<96>(tq, td, p, stream);
+    case 32: return bc == 64 ? launch_attention_bwd<32, 64>(tq, td, tqc, tdc, p, stream) : launch_attention_bwd<32, 128>(tq, td, tqc, tdc, p, stream);
+    case 48: return bc == 64 ? launch_attention_bwd<48, 64>(tq, td, tqc, tdc, p, stream) : launch_attention_bwd<48, 128>(tq, td, tqc, tdc, p, stream);
+    case 64: return launch_attention_bwd<64, 128>(tq, td, tqc, tdc, p, stream);
+    case 80: return launch_attention_bwd<80, 128>(tq, td, tqc, tdc, p, stream);
+    case 96: return launch_attention_bwd<96, 128>(tq, td, tqc, tdc, p, stream);
     default: return fail(B200_ERR_UNSUPPORTED, "attention_bwd: head_dim %d unsupported (32/48/64/80/96)", head_dim);
   }
 }
