@@ -275,7 +275,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     // ============================================================ softmax (row = thread)
     const int row = warp * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    const bool packed = (p.variant & 4) == 0;
+    // Exponentials: two per MUFU op in bf16 (ex2.approx.ftz.bf16x2) or one per op in fp32.  Measured on B200 at
+    // b16 s1000 d32: with 128-column tiles (2 CTAs/SM) the packed form wins; with 64-column tiles (4 CTAs/SM) the
+    // fp32 form does (59.3 vs 63.4 us) and is more accurate (2.3e-3 vs 3.1e-3 rel-L2).  Moving part of the
+    // exponentials to an FMA-pipe polynomial (FlashAttention-4) or replacing F2FP by integer packing made this kernel
+    // SLOWER (80 / 66 us): ncu shows it bound by the tcgen05.ld -> exp -> st.shared dependency chain of each thread
+    // (long-scoreboard + fixed-latency stalls, issue slots 39 % busy), not by the XU pipe.  variant bit 2 flips the default.
+    const bool packed = ((p.variant & 4) == 0) != (KV == 64);
     uint8_t* sp_row = sP + row * 16;
     float ref = 0.f;                              // reference maximum, in exponent units: m_ref * scale * log2(e)
     for (int j = 0; j < p.nblk; ++j) {
