@@ -81,6 +81,7 @@ class AudioLDMPipeline:
         # per-tile latency on already-occupied SMs, not by idle SMs, so one chain is the default.
         self.branches = int(os.environ.get("B200_BRANCHES", "1")) if branches is None else int(branches)
         self._loops: Dict[tuple, _LoopState] = {}
+        self._tail_graphs: Dict[tuple, Optional[tuple]] = {}
         if self.vae is not None:
             self.vae = self.vae.to(self.device, tail_dtype).eval()
         if self.vocoder is not None:
@@ -250,6 +251,37 @@ class AudioLDMPipeline:
             wave = self.vocoder(mel.to(self.tail_dtype))
         return wave.cpu().float()
 
+    def latents_to_waveform(self, latents: Tensor) -> Tensor:
+        """VAE decode + vocoder on the device (the reference path's torch kernels, unchanged), replayed from a CUDA
+        graph per latent shape: the tail is ~1800 small eager launches, i.e. launch-bound.  Falls back to eager
+        launches if a foreign VAE / vocoder cannot be captured.  Returns the device waveform [B, samples]."""
+        key = (tuple(latents.shape), self.tail_dtype)
+        ent = self._tail_graphs.get(key) if self.use_cuda_graph and latents.is_cuda else None
+        if ent is None and self.use_cuda_graph and latents.is_cuda and key not in self._tail_graphs:
+            try:
+                z = torch.zeros_like(latents, dtype=torch.float32)
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s), torch.no_grad():
+                    for _ in range(2):                  # warm-up: cuDNN algorithm selection happens outside capture
+                        self.vocoder(self.decode_latents(z).squeeze(1).to(self.tail_dtype))
+                torch.cuda.current_stream().wait_stream(s)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g), torch.no_grad():
+                    out = self.vocoder(self.decode_latents(z).squeeze(1).to(self.tail_dtype))
+                ent = self._tail_graphs[key] = (g, z, out)
+            except Exception:                           # noqa: BLE001 -- the tail is not the B200 path: eager is equivalent
+                torch.cuda.synchronize()
+                ent = self._tail_graphs[key] = None
+        if ent is None:
+            with torch.no_grad():
+                mel = self.decode_latents(latents)
+                return self.vocoder(mel.squeeze(1).to(self.tail_dtype))
+        g, z, out = ent
+        z.copy_(latents)
+        g.replay()
+        return out
+
     # ------------------------------------------------------------------ __call__
     @torch.no_grad()
     def __call__(self, prompt=None, audio_length_in_s: Optional[float] = None, num_inference_steps: int = 10,
@@ -279,8 +311,7 @@ class AudioLDMPipeline:
             return AudioPipelineOutput(audios=lat) if return_dict else (lat,)
         if self.vae is None or self.vocoder is None:
             raise ValueError("pipeline was built without vae/vocoder: use output_type='latent'")
-        mel = self.decode_latents(lat)
-        audio = self.mel_spectrogram_to_waveform(mel)[:, :original_waveform_length]
+        audio = self.latents_to_waveform(lat).cpu().float()[:, :original_waveform_length]
         if output_type == "np":
             audio = audio.numpy()
         elif output_type != "pt":
