@@ -33,6 +33,8 @@ _PROTOS = {
     "b200_conv_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "b200_linear_lora": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                 c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "b200_groupnorm_silu": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
                                     c_int, c_void_p, c_void_p]),
     "b200_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),

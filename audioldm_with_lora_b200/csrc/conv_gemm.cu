@@ -85,6 +85,13 @@ struct ConvGemmParams {
   int a_rank2;                      // linear layers (W = 1, one image): A tensor maps are plain 2-D [rows, K]
   int debug;                        // profiling knobs (env B200_GEMM_DEBUG): 1 = no TMA after the first fill of each
                                     // stage, 2 = no MMA (results are garbage; timing experiments only)
+  // Fused LoRA down-projection (linear layers, 1-CTA mode): phase 0 of every tile computes T = x . A^T (N = lora_n) on the
+  // tensor core into TMEM columns [2 block_n, 2 block_n + lora_n); the epilogue warps turn it into a bf16 K-major
+  // shared-memory tile while the base k-blocks run; the LoRA k-block (segment 1) then takes that tile as its A operand.
+  int lora_n;                       // 0: off; else 16 / 32 / 48 / 64
+  int lora_kb;                      // k-blocks of phase 0 (= c0 / 64)
+  int m_rows;                       // rows of the token matrix (bounds the optional global copy of T)
+  __nv_bfloat16* t_out;             // optional [m_rows, 64] copy of T (the fine-tuning step keeps it for dB)
 };
 
 // exact-erf GELU to ~2e-7 absolute (Abramowitz-Stegun 7.1.26 erfc; bf16 output rounding is 4e-3 relative):
@@ -118,24 +125,28 @@ __device__ __forceinline__ void add8(float (&v)[8], const float* src) {
   v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
 }
 
-template <bool kCta2>
+template <bool kCta2, bool kLora = false>
 __global__ void __launch_bounds__(kThreads, 1)      // 10 warps are allocated as 12: 168 registers per thread at most
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmOut, const ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmLA,
+                 const ConvGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024B alignment for the 128B swizzle atoms.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t cta_rank = kCta2 ? cluster_ctarank() : 0u;       // 0 = leader of the pair
   const int b_rows = kCta2 ? p.block_n / 2 : p.block_n;           // weight rows this CTA stages per k-block
   const int stage_bytes = kABytes + b_rows * kBlockK * 2;
-  uint8_t* epi_smem = smem + p.stages * stage_bytes;
+  uint8_t* t_tile = smem + p.stages * stage_bytes;                 // [128 rows][64 bf16], 128B-swizzled (fused LoRA only)
+  uint8_t* epi_smem = t_tile + (kLora ? kABytes : 0);
   float* epi_vec = reinterpret_cast<float*>(epi_smem + kEpiWarps * kEpiStageBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * (kEpiStageBytes + kEpiVecBytes));
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* lt_tmem_bar = tempty_bar + 2;                          // phase-0 accumulator complete (MMA -> epilogue warps)
+  uint64_t* lt_smem_bar = lt_tmem_bar + 1;                         // T tile written (4 epilogue warps -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lt_smem_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -156,6 +167,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], kCta2 ? 2 * kEpiWarps : kEpiWarps);   // one arrival per epilogue warp (of both CTAs)
     }
+    mbar_init(lt_tmem_bar, 1);
+    mbar_init(lt_smem_bar, 4);
+    if (kLora) tma_prefetch_desc(&tmLA);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -211,6 +225,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         else cb = kb_begin - (seg == 1 ? p.seg_end0 : p.seg_end1);
         int dh = 0, dw = 0;
         if (seg == 0 && p.ntaps == 9) { dh = tap / 3 - 1; dw = tap - (tap / 3) * 3 - 1; }
+        if (kLora) {
+          // ---- phase 0: the tile's activations (A slot) and the stacked lora_A rows (B slot), c0 / 64 k-blocks
+          const uint32_t bytes0 = do_a ? static_cast<uint32_t>(kABytes) : static_cast<uint32_t>(p.lora_n) * kBlockK * 2;
+          for (int kb = 0; kb < p.lora_kb; ++kb) {
+            if (fills >= p.stages) mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* dst = smem + s * stage_bytes;
+            uint64_t* fb = &full_bar[s];
+            ++fills;
+            if (do_a && do_b) {
+              mbar_expect_tx(fb, static_cast<uint32_t>(kABytes) + static_cast<uint32_t>(p.lora_n) * kBlockK * 2);
+              tma_load_4d(dst, &tmA0, fb, kb * kBlockK, 0, h0, n0);
+              tma_load_2d(dst + kABytes, &tmLA, fb, kb * kBlockK, 0);
+            } else {
+              mbar_expect_tx(fb, bytes0);
+              if (do_a) tma_load_4d(dst, &tmA0, fb, kb * kBlockK, 0, h0, n0);
+              else tma_load_2d(dst + kABytes, &tmLA, fb, kb * kBlockK, 0);
+            }
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+          }
+        }
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           // (a look-ahead test_wait on the next stage was measured: slower -- the producer usually runs ahead, the
           //  poll fails and the blocking wait still follows)
@@ -224,8 +258,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if ((p.debug & 1) && ph) {                       // timing experiment: operands stay whatever is in smem
             if (cta_rank == 0) mbar_arrive(fb);
           } else {
-            if (expect) mbar_expect_tx(fb, my_bytes);
-            if (do_a) {
+            const bool lora_block = kLora && seg == 1;     // its A operand is the T tile in shared memory
+            if (expect) mbar_expect_tx(fb, lora_block ? my_bytes - (do_a ? static_cast<uint32_t>(kABytes) : 0u) : my_bytes);
+            if (do_a && !lora_block) {
               // (three literal tensor-map operands: selecting the map through a pointer variable is slower)
               const int c0 = cb * kBlockK;
               if (kCta2) {
@@ -276,6 +311,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       for (int t = tile0; t < num_tiles; t += tile_step, ++it) {
         const int buf = it & 1;
         const uint32_t use = it >> 1;
+        if (kLora) {
+          // ---- phase 0: T = x . A^T into its own TMEM columns (no dependence on the accumulator buffers)
+          const uint32_t idesc_t = make_idesc_bf16(kBlockM, p.lora_n, 0, 0);
+          const uint32_t t_tmem = tmem_base + 2 * p.block_n;
+          for (int kb = 0; kb < p.lora_kb; ++kb) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            umma_bf16_ss(t_tmem, a_desc, b_desc, idesc_t, kb != 0);
+            umma_bf16_ss(t_tmem, a_desc + 2, b_desc + 2, idesc_t, 1);
+            umma_bf16_ss(t_tmem, a_desc + 4, b_desc + 4, idesc_t, 1);
+            umma_bf16_ss(t_tmem, a_desc + 6, b_desc + 6, idesc_t, 1);
+            umma_commit(&empty_bar[s]);
+            a_desc += desc_step;
+            b_desc += desc_step;
+            if (++s == p.stages) { s = 0; ph ^= 1; a_desc = a_desc0; b_desc = b_desc0; }
+          }
+          umma_commit(lt_tmem_bar);
+        }
         mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * p.block_n;
@@ -299,7 +352,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (prof) { const long long now = clock64(); acc_test += now - tq; tq = now; }
           tc_fence_after();
           if (prof) { const long long now = clock64(); acc_fence += now - tq; tq = now; }
-          if (!(p.debug & 2)) {
+          if (kLora && kb == p.seg_end0) {
+            // the LoRA k-block: A = T (written by the epilogue warps during the base k-blocks), B = s.B from the ring
+            mbar_wait(lt_smem_bar, it & 1);
+            tc_fence_after();
+            const uint64_t t_desc = make_smem_desc(smem_u32(t_tile), 16, 1024, SWZ_128B);
+            const uint32_t acc0 = kb != kb_begin;
+            umma_bf16_ss(d_tmem, t_desc, b_desc, idesc, acc0);
+            umma_bf16_ss(d_tmem, t_desc + 2, b_desc + 2, idesc, 1);
+            umma_bf16_ss(d_tmem, t_desc + 4, b_desc + 4, idesc, 1);
+            umma_bf16_ss(d_tmem, t_desc + 6, b_desc + 6, idesc, 1);
+            umma_commit(&empty_bar[s]);
+          } else if (!(p.debug & 2)) {
             const uint32_t acc0 = kb != kb_begin;
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
             if (kCta2) {
@@ -406,6 +470,46 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       };
       if (hf < nchunks) prefetch(hf);
 #endif
+      if (kLora && hf == 0) {
+        // ---- T (fp32, TMEM) -> bf16 K-major 128B-swizzled shared-memory tile (+ optional global copy for the backward)
+        mbar_wait(lt_tmem_bar, it & 1);
+        tc_fence_after();
+        const uint32_t t_src = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * p.block_n;
+        uint32_t pk[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pk[j] = 0u;
+        for (int c16 = 0; c16 < p.lora_n / 16; ++c16) {
+          uint32_t r[16];
+          tmem_ld_x16(t_src + c16 * 16, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t v = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            // (c16 is not a compile-time constant: select the destination words without dynamic register indexing)
+            if (c16 == 0) pk[j] = v; else if (c16 == 1) pk[8 + j] = v; else if (c16 == 2) pk[16 + j] = v; else pk[24 + j] = v;
+          }
+        }
+        const uint32_t t_row_addr = smem_u32(t_tile) + row * 128;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t addr = t_row_addr + ((g ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
+                       "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3])
+                       : "memory");
+        }
+        if (p.t_out != nullptr) {
+          const int grow = m_tile * kBlockM + row;        // linear layers: one image, W = 1, 128 rows per tile
+          if (n_tile == 0 && grow < p.m_rows) {
+            uint4* dst = reinterpret_cast<uint4*>(p.t_out + static_cast<size_t>(grow) * 64);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) dst[g] = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(lt_smem_bar);
+      }
       mbar_wait(&tfull_bar[buf], use & 1);
       if (warp == 2 && lane == 0) TL(12);
       tc_fence_after();
@@ -686,18 +790,55 @@ extern "C" int b200_debug_timeline(unsigned long long* host_out, int n) {
   return e == cudaSuccess ? B200_OK : fail(B200_ERR_CUDA, "debug_timeline: %s", cudaGetErrorString(e));
 }
 
+static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const void* a2, int c2, int nb, int h,
+                          int w, int ntaps, int stride, const void* wpacked, int n_pad, int n_valid,
+                          const float* bias, const float* rowvec, int rowvec_ld, const void* residual, int res_ld,
+                          void* out, int out_ld, int out_fp32, int geglu, int block_n, int max_ctas,
+                          int ksplit, float* workspace, int cta_pair, const void* lora_down, int lora_rows, void* t_out,
+                          void* stream_v);
+
 // C-ABI: see include/b200ldm.h
 extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, const void* a2, int c2, int nb, int h,
                               int w, int ntaps, int stride, const void* wpacked, int n_pad, int n_valid,
                               const float* bias, const float* rowvec, int rowvec_ld, const void* residual, int res_ld,
                               void* out, int out_ld, int out_fp32, int geglu, int block_n, int max_ctas,
                               int ksplit, float* workspace, int cta_pair, void* stream_v) {
+  return conv_gemm_impl(a0, c0, a1, c1, a2, c2, nb, h, w, ntaps, stride, wpacked, n_pad, n_valid, bias, rowvec, rowvec_ld,
+                        residual, res_ld, out, out_ld, out_fp32, geglu, block_n, max_ctas, ksplit, workspace, cta_pair,
+                        nullptr, 0, nullptr, stream_v);
+}
+
+// Linear layer with the rank-r LoRA branch computed INSIDE the kernel (peft lora.Linear, unmerged):
+//   out = x . W^T + (x . A^T) . (s B)^T (+ bias + residual)
+// x bf16 [m, c]; wpacked bf16 [n_pad, c + 64] = [W | s.B padded to 64 columns]; lora_down bf16 [64, c] = the stacked
+// lora_A rows (lora_rows of them valid, the rest zero).  t_out (nullable): bf16 [m, 64] copy of T = x . A^T.
+extern "C" int b200_linear_lora(const void* x, int c, int m, const void* wpacked, int n_pad, int n_valid, const float* bias,
+                                const void* residual, int res_ld, void* out, int out_ld, int block_n, int max_ctas,
+                                const void* lora_down, int lora_rows, void* t_out, void* stream_v) {
+  B200_CHECK_ARG(lora_down && lora_rows > 0 && lora_rows <= 64, "linear_lora: lora_down / lora_rows (%d) invalid", lora_rows);
+  return conv_gemm_impl(x, c, nullptr, 64, nullptr, 0, 1, m, 1, 1, 1, wpacked, n_pad, n_valid, bias, nullptr, 0, residual, res_ld,
+                        out, out_ld, 0, 0, block_n, max_ctas, 1, nullptr, 0, lora_down, lora_rows, t_out, stream_v);
+}
+
+static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const void* a2, int c2, int nb, int h,
+                          int w, int ntaps, int stride, const void* wpacked, int n_pad, int n_valid,
+                          const float* bias, const float* rowvec, int rowvec_ld, const void* residual, int res_ld,
+                          void* out, int out_ld, int out_fp32, int geglu, int block_n, int max_ctas,
+                          int ksplit, float* workspace, int cta_pair, const void* lora_down, int lora_rows, void* t_out,
+                          void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const bool fused_lora = lora_down != nullptr;
+  if (fused_lora) {
+    B200_CHECK_ARG(ntaps == 1 && nb == 1 && w == 1 && stride == 1 && ksplit <= 1 && !geglu && !out_fp32 && c1 == 64 && !a1 &&
+                   c2 == 0, "linear_lora: needs a plain linear layer with a 64-column LoRA segment");
+    B200_CHECK_ARG(2 * block_n + 64 <= 512, "linear_lora: block_n %d leaves no TMEM columns for T", block_n);
+    cta_pair = 0;
+  }
   B200_CHECK_ARG(stride == 1 || (stride == 2 && ntaps == 9 && !residual), "conv_gemm: stride %d unsupported", stride);
   B200_CHECK_ARG(a0 && wpacked && out, "conv_gemm: null pointer");
   B200_CHECK_ARG(ntaps == 1 || ntaps == 9, "conv_gemm: ntaps must be 1 or 9 (got %d)", ntaps);
   B200_CHECK_ARG(c0 > 0 && c0 % 64 == 0 && c1 % 64 == 0 && c2 % 64 == 0, "conv_gemm: channels must be multiples of 64 (%d,%d,%d)", c0, c1, c2);
-  B200_CHECK_ARG((c1 == 0) == (a1 == nullptr) && (c2 == 0) == (a2 == nullptr), "conv_gemm: segment pointer/channel mismatch");
+  B200_CHECK_ARG(((c1 == 0) == (a1 == nullptr) || fused_lora) && (c2 == 0) == (a2 == nullptr), "conv_gemm: segment pointer/channel mismatch");
   B200_CHECK_ARG(block_n >= 32 && block_n <= 256 && block_n % 32 == 0, "conv_gemm: block_n %d unsupported", block_n);
   B200_CHECK_ARG(n_pad % block_n == 0, "conv_gemm: n_pad %d not a multiple of block_n %d", n_pad, block_n);
   B200_CHECK_ARG(n_valid % 8 == 0 && n_valid <= (geglu ? n_pad / 2 : n_pad), "conv_gemm: n_valid %d invalid", n_valid);
@@ -740,8 +881,14 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
     p.bias = nullptr; p.rowvec = nullptr; p.residual = nullptr;
     p.out = workspace; p.out_ld = n_pad; p.out_fp32 = 1; p.tma_out = 0;
   }
+  if (fused_lora) {
+    p.lora_n = (lora_rows + 15) / 16 * 16;
+    p.lora_kb = c0 / 64;
+    p.m_rows = h;
+    p.t_out = reinterpret_cast<__nv_bfloat16*>(t_out);
+  }
   int tc = 32;
-  while (tc < 2 * block_n) tc *= 2;
+  while (tc < 2 * block_n + p.lora_n) tc *= 2;
   p.tmem_cols = tc;
   // 2-CTA pairs: needs two halves of >= 64 weight rows and more than one m-tile to pair up
   // (worth its longer prologue / cluster syncs only when the k-loop dominates)
@@ -749,7 +896,8 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
   p.num_m_groups = cta2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
   const int b_rows = cta2 ? block_n / 2 : block_n;
   const int stage_bytes = kABytes + b_rows * kBlockK * 2;
-  const int fixed = kEpiWarps * (kEpiStageBytes + kEpiVecBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+  const int fixed = kEpiWarps * (kEpiStageBytes + kEpiVecBytes) + 1024 /*align slack*/ + 256 /*barriers*/ +
+                    (fused_lora ? kABytes : 0) /*T tile*/;
   p.stages = (kSmemLimit - fixed) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   static const int dbg_stages = getenv("B200_GEMM_STAGES") ? atoi(getenv("B200_GEMM_STAGES")) : 0;
@@ -758,7 +906,7 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
   p.debug = dbg_flags;
   const int smem_bytes = p.stages * stage_bytes + fixed;
 
-  CUtensorMap tA[3], tB, tO;
+  CUtensorMap tA[3], tB, tO, tLA;
   const void* srcs[3] = {a0, a1 ? a1 : a0, a2 ? a2 : a0};
   const int chans[3] = {c0, c1 ? c1 : c0, c2 ? c2 : c0};
   p.a_rank2 = 0;     // plain 2-D maps for linear layers were measured: no difference to the 4-D box
@@ -786,6 +934,15 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
     int rc = make_tmap_bf16(&tB, wpacked, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
+  if (fused_lora) {
+    uint64_t dims[2] = {(uint64_t)c0, 64};
+    uint64_t strides[1] = {(uint64_t)c0};
+    uint32_t box[2] = {64, (uint32_t)p.lora_n};
+    int rc = make_tmap_bf16(&tLA, lora_down, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  } else {
+    tLA = tB;
+  }
   if (p.tma_out) {
     // each epilogue warp stores its 32 accumulator rows x 64 columns: box = (64, bw, bh, bn), w fastest
     const int bw = w < 32 ? w : 32;
@@ -807,20 +964,25 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaFuncSetAttribute(conv_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaFuncSetAttribute(conv_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaFuncSetAttribute(conv_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   }
   int grid = p.num_m_groups * p.num_n_tiles * p.ksplit;
   int cap = max_ctas > 0 ? max_ctas : num_sms;
   if (cta2) {
     if (grid > cap / 2) grid = cap / 2;
     if (grid < 1) grid = 1;
-    B200_CHECK_PDL("conv_gemm(2-CTA)", launch_pdl(conv_gemm_kernel<true>, dim3(2 * grid), dim3(kThreads), (size_t)smem_bytes,
-                                                  stream, 2, tA[0], tA[1], tA[2], tB, tO, p));
+    B200_CHECK_PDL("conv_gemm(2-CTA)", launch_pdl(conv_gemm_kernel<true, false>, dim3(2 * grid), dim3(kThreads), (size_t)smem_bytes,
+                                                  stream, 2, tA[0], tA[1], tA[2], tB, tO, tLA, p));
   } else {
     if (grid > cap) grid = cap;
-    B200_CHECK_PDL("conv_gemm", launch_pdl(conv_gemm_kernel<false>, dim3(grid), dim3(kThreads), (size_t)smem_bytes, stream,
-                                           0, tA[0], tA[1], tA[2], tB, tO, p));
+    if (fused_lora)
+      B200_CHECK_PDL("linear_lora", launch_pdl(conv_gemm_kernel<false, true>, dim3(grid), dim3(kThreads), (size_t)smem_bytes,
+                                               stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+    else
+      B200_CHECK_PDL("conv_gemm", launch_pdl(conv_gemm_kernel<false, false>, dim3(grid), dim3(kThreads), (size_t)smem_bytes,
+                                             stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
   }
   if (p.ksplit > 1) {
     const size_t total = m_total * (n_valid / 8);

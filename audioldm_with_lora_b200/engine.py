@@ -139,14 +139,15 @@ class UNetEngine:
             self._plans[key]["sms"] = sms
         return self._plans[key]
 
-    def _pw(self, segs, bias, m_tiles, ntaps, c0, c1=0, c2=0, geglu=False, block_n=None, split=True) -> PackedWeight:
+    def _pw(self, segs, bias, m_tiles, ntaps, c0, c1=0, c2=0, geglu=False, block_n=None, split=True,
+            max_bn: int = 256) -> PackedWeight:
         n = segs[0].shape[0]
         num_kb = (ntaps * c0 + c1 + c2) // 64
         if block_n:
             bn, ks = block_n, 1
         else:
             bn, ks = ops.choose_tiling(n, m_tiles, num_kb, geglu, allow_split=split,
-                                       num_sms=getattr(self, "_tiling_sms", ops.NUM_SMS))
+                                       num_sms=getattr(self, "_tiling_sms", ops.NUM_SMS), max_bn=max_bn)
         return packing.pack(segs, bias, bn, ntaps, c0, c1, c2, geglu, device=self.device, ksplit=ks)
 
     def _build_plan(self, nb: int, h: int, w: int) -> dict:
@@ -249,7 +250,11 @@ class UNetEngine:
                     r_tot = sum(x.shape[0] for x in a_list if x is not None)
                     W[p + ".lora_down_qkv"] = packing.pack_lora_down(a_list, c, device=self.device)
                     W[p + ".lora_down_qkv"].alg_macs_per_row = float(r_tot * c)
-                    W[p + ".qkv"] = self._pw([wqkv, seg], None, mt, 1, c, kp)
+                    W[p + ".lora_down_qkv"].lora_rows = r_tot
+                    fuse = ops.lora_fusion_pays(3 * c, mt, kp, getattr(self, "_tiling_sms", ops.NUM_SMS))
+                    W[p + ".qkv"] = self._pw([wqkv, seg], None, mt, 1, c, kp, split=not fuse,
+                                             max_bn=ops.LORA_FUSED_MAX_BN if fuse else 256)
+                    W[p + ".qkv"].lora_fused = fuse
                     W[p + ".qkv"].alg_macs_per_row = float(3 * c * c + r_tot * c)
                 else:
                     W.pop(p + ".lora_down_qkv", None)
@@ -261,7 +266,11 @@ class UNetEngine:
                     seg = packing.lora_up_segment([eo.B], [eo.A], [eo.scaling * self.lora_scale], c)
                     W[p + ".lora_down_o"] = packing.pack_lora_down([eo.A], c, device=self.device)
                     W[p + ".lora_down_o"].alg_macs_per_row = float(eo.A.shape[0] * c)
-                    W[p + ".to_out"] = self._pw([wo, seg], bo, mt, 1, c, kp)
+                    W[p + ".lora_down_o"].lora_rows = eo.A.shape[0]
+                    fuse = ops.lora_fusion_pays(c, mt, kp, getattr(self, "_tiling_sms", ops.NUM_SMS))
+                    W[p + ".to_out"] = self._pw([wo, seg], bo, mt, 1, c, kp, split=not fuse,
+                                                max_bn=ops.LORA_FUSED_MAX_BN if fuse else 256)
+                    W[p + ".to_out"].lora_fused = fuse
                     W[p + ".to_out"].alg_macs_per_row = float(c * c + eo.A.shape[0] * c)
                 else:
                     W.pop(p + ".lora_down_o", None)
@@ -538,6 +547,11 @@ class _Runner:
         self.ar.release(ws)
         return out
 
+    def linear_lora(self, name, down, a0, lvl, *, residual=None):
+        pw = self.W[name]
+        out = self.ar.alloc((self.M(lvl), pw.n_valid), torch.bfloat16)
+        return ops.linear_lora(pw, down, a0, self.M(lvl), out, residual=residual, max_ctas=self.max_ctas)
+
     def resnet(self, r: ResnetDesc, x0, x1, lvl):
         c_h = r.cin - r.skip_c
         n1 = self.gn(x0, c_h, x1, r.skip_c, lvl, r.name + ".norm1", 1e-5, True)
@@ -555,9 +569,13 @@ class _Runner:
     def attention(self, p, x, lvl, c):
         """x: LayerNorm output [M, c] -> attention output (before to_out)."""
         hh, ww = self.sizes[lvl]
-        T = self.linear(p + ".lora_down_qkv", x, lvl) if p + ".lora_down_qkv" in self.W else None
-        qkv = self.linear(p + ".qkv", x, lvl, a1=T)
-        self.ar.release(T)
+        down = self.W.get(p + ".lora_down_qkv")
+        if ops.linear_lora_ok(self.W[p + ".qkv"], down):
+            qkv = self.linear_lora(p + ".qkv", down, x, lvl)       # T = x . A^T never leaves the SM
+        else:
+            T = self.linear(p + ".lora_down_qkv", x, lvl) if down is not None else None
+            qkv = self.linear(p + ".qkv", x, lvl, a1=T)
+            self.ar.release(T)
         ao = self.ar.alloc((self.M(lvl), c), torch.bfloat16)
         ops.attention(qkv, ao, self.nb, hh * ww, self.cfg.heads, c // self.cfg.heads, variant=self.eng.attn_variant)
         self.ar.release(qkv)
@@ -587,9 +605,14 @@ class _Runner:
                 continue
             ao = self.attention(p, ln, lvl, c)
             ar.release(ln)
-            To = self.linear(p + ".lora_down_o", ao, lvl) if p + ".lora_down_o" in W else None
-            new_tok = self.linear(p + ".to_out", ao, lvl, a1=To, residual=tok)
-            ar.release(To); ar.release(ao); ar.release(tok)
+            down_o = W.get(p + ".lora_down_o")
+            if ops.linear_lora_ok(W[p + ".to_out"], down_o):
+                new_tok = self.linear_lora(p + ".to_out", down_o, ao, lvl, residual=tok)
+            else:
+                To = self.linear(p + ".lora_down_o", ao, lvl) if down_o is not None else None
+                new_tok = self.linear(p + ".to_out", ao, lvl, a1=To, residual=tok)
+                ar.release(To)
+            ar.release(ao); ar.release(tok)
             tok = new_tok
         ln = ar.alloc((M, c), torch.bfloat16)
         ops.layernorm(tok, M, c, S[b + ".norm3.weight"], S[b + ".norm3.bias"], 1e-5, ln)

@@ -94,7 +94,7 @@ def _kb_cycles(bn: int, pair: bool = False) -> float:
 
 
 def choose_tiling(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_split: bool = True,
-                  num_sms: int = NUM_SMS) -> Tuple[int, int]:
+                  num_sms: int = NUM_SMS, max_bn: int = 256) -> Tuple[int, int]:
     """(block_n, ksplit) minimising a wave/cycle model on `num_sms` SMs (148, or this chain's share of them when
     several sub-batch chains run concurrently); split-K only when it wins by > 25 %."""
     step = 128 if geglu else 64
@@ -102,7 +102,7 @@ def choose_tiling(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_
     for ks in (1, 2, 3, 4):
         if ks > 1 and (not allow_split or geglu or num_kb < 16 * ks // 2):
             continue
-        for bn in range(step, 257, step):
+        for bn in range(step, max_bn + 1, step):
             pair = CTA_PAIR and bn % 128 == 0 and m_tiles >= 2 and num_kb >= 16
             tiles1 = (2 * math.ceil(m_tiles / 2) if pair else m_tiles) * math.ceil(n / bn)
             if ks > 1 and tiles1 > num_sms // 2:
@@ -147,6 +147,41 @@ def conv_gemm(pw: PackedWeight, a0: Tensor, nb: int, h: int, w: int, out: Tensor
          nb, h, w, pw.ntaps, stride, ptr(pw.w), pw.n_pad, pw.n_valid, ptr(pw.bias), ptr(rowvec), rowvec_ld,
          ptr(residual), res_ld, ptr(out), ld, int(out_fp32), int(pw.geglu), pw.block_n, max_ctas, ksplit,
          ptr(workspace) if ksplit > 1 else None, (int(CTA_PAIR) if cta_pair is None else (2 if cta_pair else 0)), stream(), info=info)
+    return out
+
+
+LORA_FUSED = os.environ.get("B200_LORA_FUSED", "1") != "0"
+LORA_FUSED_MAX_BN = 192          # 2 * block_n accumulator columns + up to 64 columns of T must fit 512 TMEM columns
+
+
+def lora_fusion_pays(n: int, m_tiles: int, kp: int, num_sms: int = NUM_SMS) -> bool:
+    """Plan-time choice.  The in-kernel down-projection costs ~3.5 us per tile (phase 0 is on the tile's critical path)
+    and caps the tile width at 192; it replaces a ~6 us launch.  Measured on B200: a win whenever a CTA runs at most
+    ~2 tiles (all level-2/3 layers, to_out at level 1), a loss for the multi-wave level-1 QKV GEMM (20.8 vs 19.8 us)."""
+    return LORA_FUSED and kp == 64 and m_tiles * math.ceil(n / LORA_FUSED_MAX_BN) <= 2 * num_sms
+
+
+def linear_lora_ok(pw: PackedWeight, down: Optional[PackedWeight]) -> bool:
+    """Can this adapted linear layer run with the LoRA down-projection inside the GEMM kernel?"""
+    return (LORA_FUSED and getattr(pw, "lora_fused", False) and down is not None and getattr(down, "lora_rows", 0) > 0 and
+            pw.c1 == 64 and pw.c2 == 0 and
+            pw.ntaps == 1 and not pw.geglu and pw.ksplit == 1 and pw.block_n <= LORA_FUSED_MAX_BN and down.n_pad == 64)
+
+
+def linear_lora(pw: PackedWeight, down: PackedWeight, x: Tensor, m: int, out: Tensor, *, residual: Optional[Tensor] = None,
+                t_out: Optional[Tensor] = None, max_ctas: int = 0) -> Tensor:
+    """out = x W^T + (x A^T)(s B)^T (+ bias + residual) in ONE launch; see include/b200ldm.h::b200_linear_lora."""
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() == m * pw.c0 and out.dtype == torch.bfloat16
+    assert down.w.shape == (64, pw.c0) and pw.c1 == 64
+    res_ld = pw.n_valid if residual is not None else 0
+    if t_out is not None:
+        assert t_out.dtype == torch.bfloat16 and t_out.numel() == m * 64
+    info = None
+    if _lib.PROFILE is not None:
+        info = {"flops": 2.0 * m * pw.macs_per_row, "m": m, "n": pw.n_valid, "k": pw.k, "bn": pw.block_n, "taps": 1,
+                "desc": "lora-fused"}
+    call("b200_linear_lora", ptr(x), pw.c0, m, ptr(pw.w), pw.n_pad, pw.n_valid, ptr(pw.bias), ptr(residual), res_ld,
+         ptr(out), pw.n_valid, pw.block_n, max_ctas, ptr(down.w), down.lora_rows, ptr(t_out), stream(), info=info)
     return out
 
 

@@ -189,8 +189,12 @@ class LoraTrainer:
                 wqkv_t = torch.cat([sd[f"{p}.{n}.weight"] for n in ("to_q", "to_k", "to_v")]).t().contiguous()   # [C, 3C]
                 if any(s is not None for s in slots):
                     kp = packing.lora_pad(sum(s.r for s in slots if s is not None))
+                    fuse = ops.lora_fusion_pays(c, mt, kp)
                     Wb[p + ".bwd_down_qkv"] = packing.pack([torch.zeros(kp, 3 * c)], None, min(64, kp), 1, 3 * c, device=self.device)
-                    Wb[p + ".bwd_qkv"] = eng._pw([wqkv_t, torch.zeros(c, kp)], None, mt, 1, 3 * c, kp)
+                    Wb[p + ".bwd_down_qkv"].lora_rows = sum(s.r for s in slots if s is not None)
+                    Wb[p + ".bwd_qkv"] = eng._pw([wqkv_t, torch.zeros(c, kp)], None, mt, 1, 3 * c, kp, split=not fuse,
+                                                 max_bn=ops.LORA_FUSED_MAX_BN if fuse else 256)
+                    Wb[p + ".bwd_qkv"].lora_fused = fuse
                     off = 0
                     for i, s in enumerate(slots):
                         if s is None:
@@ -211,8 +215,12 @@ class LoraTrainer:
                 if so is not None:
                     kp = packing.lora_pad(so.r)
                     sc = so.scaling * self.lora_scale
+                    fuse = ops.lora_fusion_pays(c, mt, kp)
                     Wb[p + ".bwd_down_o"] = packing.pack([torch.zeros(kp, c)], None, min(64, kp), 1, c, device=self.device)
-                    Wb[p + ".bwd_to_out"] = eng._pw([wo_t, torch.zeros(c, kp)], None, mt, 1, c, kp)
+                    Wb[p + ".bwd_down_o"].lora_rows = so.r
+                    Wb[p + ".bwd_to_out"] = eng._pw([wo_t, torch.zeros(c, kp)], None, mt, 1, c, kp, split=not fuse,
+                                                    max_bn=ops.LORA_FUSED_MAX_BN if fuse else 256)
+                    Wb[p + ".bwd_to_out"].lora_fused = fuse
                     refresh.append((W[p + ".lora_down_o"].w, 0, 0, so.off_a, so.r, so.c, 0, 1.0))
                     refresh.append((W[p + ".to_out"].w, 0, c, so.off_b, so.c, so.r, 0, sc))
                     refresh.append((Wb[p + ".bwd_down_o"].w, 0, 0, so.off_b, so.c, so.r, 1, sc))
@@ -308,13 +316,25 @@ class LoraTrainer:
                 p = f"{b}.{a}"
                 ln = ar.alloc((m, c), bf16)
                 ops.layernorm(tok, m, c, S[f"{b}.{ln_name}.weight"], S[f"{b}.{ln_name}.bias"], 1e-5, ln)
-                T = gemm(W[p + ".lora_down_qkv"], ln, lvl) if p + ".lora_down_qkv" in W else None
-                qkv = gemm(W[p + ".qkv"], ln, lvl, a1=T)
+                down = W.get(p + ".lora_down_qkv")
+                if ops.linear_lora_ok(W[p + ".qkv"], down):      # T = ln . A^T computed inside the QKV GEMM, kept for dB
+                    T = ar.alloc((m, 64), bf16)
+                    qkv = ar.alloc((m, 3 * c), bf16)
+                    ops.linear_lora(W[p + ".qkv"], down, ln, m, qkv, t_out=T)
+                else:
+                    T = gemm(down, ln, lvl) if down is not None else None
+                    qkv = gemm(W[p + ".qkv"], ln, lvl, a1=T)
                 ao = ar.alloc((m, c), bf16)
                 lse = ar.alloc((nb, cfg.heads, hh * ww), f32)
                 ops.attention_lse(qkv, ao, lse, nb, hh * ww, cfg.heads, c // cfg.heads)
-                To = gemm(W[p + ".lora_down_o"], ao, lvl) if p + ".lora_down_o" in W else None
-                new_tok = gemm(W[p + ".to_out"], ao, lvl, a1=To, residual=tok)
+                down_o = W.get(p + ".lora_down_o")
+                if ops.linear_lora_ok(W[p + ".to_out"], down_o):
+                    To = ar.alloc((m, 64), bf16)
+                    new_tok = ar.alloc((m, c), bf16)
+                    ops.linear_lora(W[p + ".to_out"], down_o, ao, m, new_tok, residual=tok, t_out=To)
+                else:
+                    To = gemm(down_o, ao, lvl) if down_o is not None else None
+                    new_tok = gemm(W[p + ".to_out"], ao, lvl, a1=To, residual=tok)
                 bc["attn"][a] = {"tok_in": tok, "ln": ln, "T": T, "qkv": qkv, "ao": ao, "lse": lse, "To": To}
                 tok = new_tok
             ln3 = ar.alloc((m, c), bf16)
@@ -458,8 +478,13 @@ class LoraTrainer:
                 so = self.slots.get(p + ".to_out.0")
                 sl = [self.slots.get(f"{p}.{n}") for n in ("to_q", "to_k", "to_v")]
                 descs: List[WgradDesc] = []
-                dTo = gemm(Wb[p + ".bwd_down_o"], d_tok, lvl) if so is not None else None
-                d_ao = gemm(Wb[p + ".bwd_to_out"], d_tok, lvl, a1=dTo)
+                if so is not None and ops.linear_lora_ok(Wb[p + ".bwd_to_out"], Wb[p + ".bwd_down_o"]):
+                    dTo = ar.alloc((m, 64), bf16)                # dT = d_tok . (s B) computed inside the dgrad GEMM
+                    d_ao = ar.alloc((m, c), bf16)
+                    ops.linear_lora(Wb[p + ".bwd_to_out"], Wb[p + ".bwd_down_o"], d_tok, m, d_ao, t_out=dTo)
+                else:
+                    dTo = gemm(Wb[p + ".bwd_down_o"], d_tok, lvl) if so is not None else None
+                    d_ao = gemm(Wb[p + ".bwd_to_out"], d_tok, lvl, a1=dTo)
                 if so is not None:
                     sc = so.scaling * self.lora_scale
                     descs.append(WgradDesc(d_tok.data_ptr(), ac["To"].data_ptr(), flat_g.data_ptr() + 4 * so.off_b,
@@ -471,7 +496,14 @@ class LoraTrainer:
                 ops.attention_bwd(ac["qkv"], ac["ao"], d_ao, ac["lse"], delta, d_qkv, nb, hh * ww, cfg.heads, c // cfg.heads)
                 ar.release(delta); ar.release(d_ao)
                 has_qkv = any(s is not None for s in sl)
-                dT = gemm(Wb[p + ".bwd_down_qkv"], d_qkv, lvl) if has_qkv else None
+                stop = (not need_dx) and a == "attn1"
+                d_ln = None
+                if has_qkv and not stop and ops.linear_lora_ok(Wb[p + ".bwd_qkv"], Wb[p + ".bwd_down_qkv"]):
+                    dT = ar.alloc((m, 64), bf16)
+                    d_ln = ar.alloc((m, c), bf16)
+                    ops.linear_lora(Wb[p + ".bwd_qkv"], Wb[p + ".bwd_down_qkv"], d_qkv, m, d_ln, t_out=dT)
+                else:
+                    dT = gemm(Wb[p + ".bwd_down_qkv"], d_qkv, lvl) if has_qkv else None
                 off = 0
                 for i, s in enumerate(sl):
                     if s is None:
@@ -485,9 +517,9 @@ class LoraTrainer:
                     off += s.r
                 if descs:
                     ops.lora_wgrad(descs, m)
-                stop = (not need_dx) and a == "attn1"
                 if not stop:
-                    d_ln = gemm(Wb[p + ".bwd_qkv"], d_qkv, lvl, a1=dT)
+                    if d_ln is None:
+                        d_ln = gemm(Wb[p + ".bwd_qkv"], d_qkv, lvl, a1=dT)
                     new_d_tok = ar.alloc((m, c), bf16)
                     ops.layernorm_bwd(ac["tok_in"], d_ln, m, c, S[f"{b}.{ln_name}.weight"], 1e-5, d_tok, new_d_tok)
                     ar.release(d_ln)

@@ -54,6 +54,17 @@ int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, const void* a
                    int out_fp32, int geglu, int block_n, int max_ctas, int ksplit, float* workspace, int cta_pair,
                    void* stream);
 
+/* Linear layer with the rank-r LoRA branch computed inside the kernel (peft lora.Linear, unmerged; LoRA config at
+ * generate_audio.py:21-29, train_audioldm_lora.py:378-385):  out = x W^T + (x A^T)(s B)^T (+ bias + residual).
+ * Phase 0 of every tile runs T = x A^T as a second, narrow tcgen05.mma into spare TMEM columns; the epilogue warps turn
+ * it into a bf16 K-major shared-memory tile while the base k-blocks stream, and the last k-block multiplies that tile
+ * with s.B -- the down-projection never leaves the SM and costs no launch of its own.  x bf16 [m, c]; wpacked bf16
+ * [n_pad, c + 64] = [W | s.B in 64 padded columns]; lora_down bf16 [64, c] (lora_rows valid stacked lora_A rows, rest
+ * zero); t_out (nullable) bf16 [m, 64]: copy of T for the backward pass.  block_n <= 192. */
+int b200_linear_lora(const void* x, int c, int m, const void* wpacked, int n_pad, int n_valid, const float* bias,
+                     const void* residual, int res_ld, void* out, int out_ld, int block_n, int max_ctas,
+                     const void* lora_down, int lora_rows, void* t_out, void* stream);
+
 /* Launch-shape hint for the calling thread: the number of SMs the following launches should size themselves for
  * (0 = all).  Used when independent sub-batch chains run concurrently on parallel streams. */
 int b200_set_sm_budget(int n);

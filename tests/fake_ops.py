@@ -58,6 +58,22 @@ def set_sm_budget(n):
     pass
 
 
+def linear_lora_ok(pw, down):
+    return (getattr(pw, "lora_fused", False) and down is not None and getattr(down, "lora_rows", 0) > 0 and pw.c1 == 64 and
+            pw.c2 == 0 and pw.ntaps == 1 and not pw.geglu and pw.ksplit == 1 and pw.block_n <= 192)
+
+
+def linear_lora(pw, down, x, m, out, *, residual=None, t_out=None, max_ctas=0):
+    xf = x.view(m, pw.c0).float()
+    T = torch.zeros(m, 64)
+    T[:, :down.lora_rows] = xf @ down.w[:down.lora_rows].float().T
+    T = T.to(bf16)
+    if t_out is not None:
+        t_out.view(m, 64).copy_(T)
+    conv_gemm(pw, x, 1, m, 1, out, a1=T, residual=residual)
+    return out
+
+
 def groupnorm_silu(x0, c0, x1, c1, nb, hw, gamma, beta, eps, silu, y, groups=32):
     x = x0.view(nb, hw, c0).float()
     if c1:
@@ -330,5 +346,5 @@ def install(monkeypatch, ops_module):
     """Replace the kernel wrappers of `ops_module` (keeps PackedWeight / tiling helpers)."""
     for name in ("conv_gemm", "groupnorm_silu", "layernorm", "attention", "time_class_embed",
                  "pack_nchw_to_nhwc", "unpack_nhwc_to_nchw", "upsample_nearest", "sampler_step", "add_noise",
-                 "adamw_flat", "mse_partial", "set_sm_budget") + TRAIN_OPS:
+                 "adamw_flat", "mse_partial", "set_sm_budget", "linear_lora_ok", "linear_lora") + TRAIN_OPS:
         monkeypatch.setattr(ops_module, name, globals()[name])
