@@ -327,8 +327,9 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: all conv/linear layers)",
                      "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                      "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
-                     "how": "sum of algorithmic FLOPs of the step's 245 conv/linear launches / sum of their per-launch device "
-                            "times (each launch replayed 8x in its own CUDA graph, CUDA events on the launching stream)",
+                     "how": f"sum of algorithmic FLOPs of the step's {cg['calls']} b200_conv_gemm launches (every conv / linear layer "
+                            "except the LoRA-adapted projections, which run in b200_linear_lora) / sum of their per-launch "
+                            "device times (each launch replayed 8x in its own CUDA graph, CUDA events on the launching stream)",
                      "launches_per_step": cg["calls"], "ms_per_step": cg["ms"], "share_of_step": cg["ms"] / total_ms,
                      "traffic": traffic,
                      "whole_step": {"achieved": unet_flops / (unet_step_ms / 1e3) / 1e12, "frac": unet_flops / (unet_step_ms / 1e3) / 1e12 / sustained}},
