@@ -128,6 +128,37 @@ def cpu_reference_arm(steps: int, warmup: int) -> dict:
             "tail_s": tail}
 
 
+def gpu_eager_arm(device, reps: int = 5) -> dict:
+    """Same-box GPU baseline: the torch-eager oracle -- the ATen ops diffusers would issue (cuDNN convs,
+    cuBLAS linears, SDPA, native GroupNorm / LayerNorm, ~5 launches per unmerged LoRA linear) -- on this GPU in bf16, one
+    CFG-doubled UNet call at the bench shape.  A reported baseline like cpu_baseline, not the product path."""
+    from audioldm_with_lora_b200 import synthetic
+    from audioldm_with_lora_b200.arch import CONFIGS
+    from audioldm_with_lora_b200.lora import parse_lora_state_dict
+    from oracle import unet_ref
+    cfg = CONFIGS["S"]
+    dt = torch.bfloat16
+    sd = {k: v.to(device, dt) for k, v in synthetic.random_unet_state_dict(cfg, seed=0).items()}
+    ad = parse_lora_state_dict(synthetic.random_lora_state_dict(cfg, RANK_LORA, fmt="peft"))
+    lora = unet_ref.LoraSet({k: (e.A.to(device, dt), e.B.to(device, dt), e.alpha) for k, e in ad.items()})
+    h = int(CLIP_S / 0.01) // 4
+    x = torch.randn(2 * BATCH, 8, h, 16, device=device, dtype=dt)
+    emb = torch.nn.functional.normalize(torch.randn(2 * BATCH, 512, device=device), dim=-1).to(dt)
+    with torch.no_grad():
+        for _ in range(3):
+            unet_ref.unet_forward(sd, unet_ref.ARCH_S, x, 500, emb, lora=lora)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            unet_ref.unet_forward(sd, unet_ref.ARCH_S, x, 500, emb, lora=lora)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"unet_step_ms": ms, "kind": "oracle port on this GPU: torch eager bf16 (cuDNN / cuBLAS / SDPA), unmerged LoRA, UNet batch 16",
+            "implied_audio_s_per_s_loop_only": BATCH * CLIP_S / (STEPS_DDIM * ms / 1e3)}
+
+
 # ------------------------------------------------------------------------------------------ B200 arm
 def build_pipeline(device, rank_seed_base: int):
     import audioldm_with_lora_b200 as b2
@@ -340,6 +371,10 @@ def main():
     if world == 1 and STEPS_DDIM >= 8:
         cb = cpu_reference_arm(4, 1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        try:
+            line["gpu_eager_baseline"] = gpu_eager_arm(device)
+        except Exception as exc:                         # noqa: BLE001 -- a baseline, never fatal for the bench line
+            line["gpu_eager_baseline"] = {"unavailable": repr(exc)[:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
