@@ -35,6 +35,11 @@ _PROTOS = {
                                c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "b200_linear_lora": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                  c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "b200_linear_ln": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p,
+                               c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                               c_void_p]),
+    "b200_linear_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
+                                  c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "b200_groupnorm_silu": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
                                     c_int, c_void_p, c_void_p]),
     "b200_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),

@@ -92,6 +92,21 @@ struct ConvGemmParams {
   int lora_kb;                      // k-blocks of phase 0 (= c0 / 64)
   int m_rows;                       // rows of the token matrix (bounds the optional global copy of T)
   __nv_bfloat16* t_out;             // optional [m_rows, 64] copy of T (the fine-tuning step keeps it for dB)
+  // Fused LayerNorm (linear layers): the GEMM runs on the RAW rows x with gamma folded into the weights; the epilogue
+  // finishes the normalisation per row:  LN(x) W^T = rstd (x (gamma o W)^T - mu g) + b',  g[n] = sum_c gamma_c W[n,c],
+  // b'[n] = sum_c beta_c W[n,c] (+ bias).  (mu, rstd) of the tile's 128 rows are computed by the epilogue warps from
+  // global memory while the main loop runs.  `bias` carries b'; ln_ga / ln_ba are g / b' of the LoRA down-projection.
+  const float* ln_stats;            // [m_rows, ln_chunks, 2]: per 64-channel chunk (sum, sum of squares) of each row of x,
+  int ln_chunks;                    //   written by the epilogue of the kernel that produced x (stat_out below)
+  int ln_c;
+  float ln_eps;
+  const float* ln_g;                // [n_pad], packed (tile-interleaved for GEGLU) like bias
+  const float* ln_ga;               // [64]
+  const float* ln_ba;               // [64]
+  // Producer side of the same fusion: the TMA-store epilogue also writes, per row and 64-column output chunk, the
+  // (sum, sum of squares) of the bf16-rounded values it stores -- fixed slots, no atomics, deterministic.
+  float* stat_out;                  // [m_total, stat_chunks, 2] or null
+  int stat_chunks;
 };
 
 // exact-erf GELU to ~2e-7 absolute (Abramowitz-Stegun 7.1.26 erfc; bf16 output rounding is 4e-3 relative):
@@ -125,7 +140,16 @@ __device__ __forceinline__ void add8(float (&v)[8], const float* src) {
   v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
 }
 
-template <bool kCta2, bool kLora = false>
+__device__ __forceinline__ void ln_affine8(float (&v)[8], const float* g, const float* b, float mu, float rs) {
+  const float4 g0 = *reinterpret_cast<const float4*>(g), g1 = *reinterpret_cast<const float4*>(g + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(b), b1 = *reinterpret_cast<const float4*>(b + 4);
+  v[0] = fmaf(v[0] - mu * g0.x, rs, b0.x); v[1] = fmaf(v[1] - mu * g0.y, rs, b0.y);
+  v[2] = fmaf(v[2] - mu * g0.z, rs, b0.z); v[3] = fmaf(v[3] - mu * g0.w, rs, b0.w);
+  v[4] = fmaf(v[4] - mu * g1.x, rs, b1.x); v[5] = fmaf(v[5] - mu * g1.y, rs, b1.y);
+  v[6] = fmaf(v[6] - mu * g1.z, rs, b1.z); v[7] = fmaf(v[7] - mu * g1.w, rs, b1.w);
+}
+
+template <bool kCta2, bool kLora = false, bool kLn = false, bool kStat = false>
 __global__ void __launch_bounds__(kThreads, 1)      // 10 warps are allocated as 12: 168 registers per thread at most
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
@@ -470,6 +494,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       };
       if (hf < nchunks) prefetch(hf);
 #endif
+      [[maybe_unused]] float ln_mu = 0.f, ln_rs = 0.f;
+      if (kLn) {
+        // ---- LayerNorm statistics of this thread's row: the producer of x left per-chunk partial sums (fixed order)
+        const int grow = m_tile * kBlockM + row;
+        float sx = 0.f, sq = 0.f;
+        if (grow < p.m_rows) {
+          const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + static_cast<size_t>(grow) * p.ln_chunks;
+          for (int ch = 0; ch < p.ln_chunks; ++ch) {
+            const float2 v = st[ch];
+            sx += v.x;
+            sq += v.y;
+          }
+        }
+        ln_mu = sx / p.ln_c;
+        ln_rs = grow < p.m_rows ? rsqrtf(fmaxf(sq / p.ln_c - ln_mu * ln_mu, 0.f) + p.ln_eps) : 0.f;
+      }
       if (kLora && hf == 0) {
         // ---- T (fp32, TMEM) -> bf16 K-major 128B-swizzled shared-memory tile (+ optional global copy for the backward)
         mbar_wait(lt_tmem_bar, it & 1);
@@ -484,7 +524,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const uint32_t v = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            float t0 = __uint_as_float(r[2 * j]), t1 = __uint_as_float(r[2 * j + 1]);
+            if (kLn) {
+              // T = LN(x) A^T = rstd (x (gamma o A)^T - mu ga) + ba.  The tile's accumulator is multiplied by rstd in the
+              // epilogue as a whole, LoRA term included, so the tile holds T / rstd here.
+              const int col = c16 * 16 + 2 * j;
+              const float inv_rs = ln_rs > 0.f ? __fdividef(1.0f, ln_rs) : 0.f;
+              t0 = fmaf(p.ln_ba[col], inv_rs, t0 - ln_mu * p.ln_ga[col]);
+              t1 = fmaf(p.ln_ba[col + 1], inv_rs, t1 - ln_mu * p.ln_ga[col + 1]);
+            }
+            const uint32_t v = pack_bf16x2(t0, t1);
             // (c16 is not a compile-time constant: select the destination words without dynamic register indexing)
             if (c16 == 0) pk[j] = v; else if (c16 == 1) pk[8 + j] = v; else if (c16 == 2) pk[16 + j] = v; else pk[24 + j] = v;
           }
@@ -612,7 +661,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
                 const int cg = gcol + g * 8;
-                if (p.bias) add8(v, p.bias + cg);
+                if (kLn) ln_affine8(v, p.ln_g + cg, p.bias + cg, ln_mu, ln_rs);
+                else if (p.bias) add8(v, p.bias + cg);
                 if (row_ok && cg < p.n_valid) {
                   if (p.rowvec) add8(v, p.rowvec + static_cast<size_t>(n) * p.rowvec_ld + cg);
                   if (p.residual) {
@@ -639,7 +689,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                   v[j] = __uint_as_float(r[g * 8 + j]);
                   gt[j] = __uint_as_float(rg[g * 8 + j]);
                 }
-                if (p.bias) {
+                if (kLn) {
+                  ln_affine8(v, p.ln_g + bcol + g * 8, p.bias + bcol + g * 8, ln_mu, ln_rs);
+                  ln_affine8(gt, p.ln_g + bcol + half + g * 8, p.bias + bcol + half + g * 8, ln_mu, ln_rs);
+                } else if (p.bias) {
                   add8(v, p.bias + bcol + g * 8);
                   add8(gt, p.bias + bcol + half + g * 8);
                 }
@@ -649,6 +702,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 for (int j = 0; j < 4; ++j) pk[hh * 16 + g * 4 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
               }
             }
+          }
+          if (kStat && row_ok && n_tile * out_cols + cc * 64 < p.n_valid) {
+            // row statistics of the values being stored (after bf16 rounding): what the consuming LayerNorm-folded GEMM needs
+            float sx = 0.f, sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float lo = bf16_lo(pk[j]), hi = bf16_hi(pk[j]);
+              sx += lo + hi;
+              sq = fmaf(lo, lo, sq);
+              sq = fmaf(hi, hi, sq);
+            }
+            const int gchunk = (n_tile * out_cols + cc * 64) >> 6;
+            reinterpret_cast<float2*>(p.stat_out)[pix * p.stat_chunks + gchunk] = make_float2(sx, sq);
           }
           // the previous TMA store of this warp must have finished reading the staging tile
           if (lane == 0) tma_store_wait_read<0>();
@@ -795,7 +861,8 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
                           const float* bias, const float* rowvec, int rowvec_ld, const void* residual, int res_ld,
                           void* out, int out_ld, int out_fp32, int geglu, int block_n, int max_ctas,
                           int ksplit, float* workspace, int cta_pair, const void* lora_down, int lora_rows, void* t_out,
-                          void* stream_v);
+                          const float* ln_g, const float* ln_ga, const float* ln_ba, float ln_eps, const float* ln_stats,
+                          float* stat_out, void* stream_v);
 
 // C-ABI: see include/b200ldm.h
 extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, const void* a2, int c2, int nb, int h,
@@ -805,7 +872,7 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
                               int ksplit, float* workspace, int cta_pair, void* stream_v) {
   return conv_gemm_impl(a0, c0, a1, c1, a2, c2, nb, h, w, ntaps, stride, wpacked, n_pad, n_valid, bias, rowvec, rowvec_ld,
                         residual, res_ld, out, out_ld, out_fp32, geglu, block_n, max_ctas, ksplit, workspace, cta_pair,
-                        nullptr, 0, nullptr, stream_v);
+                        nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, nullptr, stream_v);
 }
 
 // Linear layer with the rank-r LoRA branch computed INSIDE the kernel (peft lora.Linear, unmerged):
@@ -817,7 +884,39 @@ extern "C" int b200_linear_lora(const void* x, int c, int m, const void* wpacked
                                 const void* lora_down, int lora_rows, void* t_out, void* stream_v) {
   B200_CHECK_ARG(lora_down && lora_rows > 0 && lora_rows <= 64, "linear_lora: lora_down / lora_rows (%d) invalid", lora_rows);
   return conv_gemm_impl(x, c, nullptr, 64, nullptr, 0, 1, m, 1, 1, 1, wpacked, n_pad, n_valid, bias, nullptr, 0, residual, res_ld,
-                        out, out_ld, 0, 0, block_n, max_ctas, 1, nullptr, 0, lora_down, lora_rows, t_out, stream_v);
+                        out, out_ld, 0, 0, block_n, max_ctas, 1, nullptr, 0, lora_down, lora_rows, t_out, nullptr, nullptr,
+                        nullptr, 0.f, nullptr, nullptr, stream_v);
+}
+
+// Any linear layer [m, c] -> [m, n] that ALSO leaves the row statistics of its (bf16) output for a following
+// LayerNorm-folded GEMM (b200_linear_ln): stat_out fp32 [m, n_valid / 64, 2] = per row and 64-column chunk (sum, sum of
+// squares).  a1 / c1: optional K segment (e.g. a LoRA T tensor); lora_down: optional in-kernel LoRA (then a1 = null).
+extern "C" int b200_linear_stats(const void* x, int c, const void* a1, int c1, int m, const void* wpacked, int n_pad,
+                                 int n_valid, const float* bias, const void* residual, int res_ld, void* out, int out_ld,
+                                 int block_n, int max_ctas, const void* lora_down, int lora_rows, float* stat_out,
+                                 void* stream_v) {
+  B200_CHECK_ARG(stat_out && n_valid % 64 == 0, "linear_stats: stat_out required, n_valid %d must be a multiple of 64", n_valid);
+  return conv_gemm_impl(x, c, a1, lora_down ? 64 : c1, nullptr, 0, 1, m, 1, 1, 1, wpacked, n_pad, n_valid, bias, nullptr, 0,
+                        residual, res_ld, out, out_ld, 0, 0, block_n, max_ctas, 1, nullptr, 0, lora_down, lora_rows, nullptr,
+                        nullptr, nullptr, nullptr, 0.f, nullptr, stat_out, stream_v);
+}
+
+// Linear layer consuming LayerNorm(x) with the LayerNorm folded in (and, optionally, the in-kernel LoRA branch):
+//   out = LN(x) W^T (+ (LN(x) A^T)(s B)^T) (+ residual), optionally through GEGLU.
+// The GEMM runs on the raw rows x with gamma folded into the packed weights (wpacked = [gamma o W | s.B]); the epilogue
+// applies rstd, the rank-1 mean correction mu * ln_g[n] and b' = `bias` (= beta W^T + the layer's bias) per row -- the
+// row statistics are computed by the epilogue warps while the main loop runs.  ln_g fp32 [n_pad] (packed order);
+// with LoRA: lora_down = gamma o A stacked [64, c], ln_ga / ln_ba fp32 [64].  Removes the LayerNorm launch and the
+// normalised activation's round trip through HBM.
+extern "C" int b200_linear_ln(const void* x, int c, int m, const void* wpacked, int n_pad, int n_valid, const float* bias,
+                              const float* ln_g, float ln_eps, const float* ln_stats, const void* residual, int res_ld,
+                              void* out, int out_ld, int geglu, int block_n, int max_ctas, const void* lora_down,
+                              int lora_rows, const float* ln_ga, const float* ln_ba, void* stream_v) {
+  B200_CHECK_ARG(bias && ln_g && ln_stats && c % 64 == 0, "linear_ln: bias (b'), ln_g and ln_stats are required");
+  B200_CHECK_ARG(!lora_down || (ln_ga && ln_ba && lora_rows > 0 && lora_rows <= 64), "linear_ln: LoRA arguments invalid");
+  return conv_gemm_impl(x, c, nullptr, lora_down ? 64 : 0, nullptr, 0, 1, m, 1, 1, 1, wpacked, n_pad, n_valid, bias, nullptr, 0,
+                        residual, res_ld, out, out_ld, 0, geglu, block_n, max_ctas, 1, nullptr, 0, lora_down, lora_rows, nullptr,
+                        ln_g, ln_ga, ln_ba, ln_eps, ln_stats, nullptr, stream_v);
 }
 
 static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const void* a2, int c2, int nb, int h,
@@ -825,12 +924,20 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
                           const float* bias, const float* rowvec, int rowvec_ld, const void* residual, int res_ld,
                           void* out, int out_ld, int out_fp32, int geglu, int block_n, int max_ctas,
                           int ksplit, float* workspace, int cta_pair, const void* lora_down, int lora_rows, void* t_out,
-                          void* stream_v) {
+                          const float* ln_g, const float* ln_ga, const float* ln_ba, float ln_eps, const float* ln_stats,
+                          float* stat_out, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const bool fused_lora = lora_down != nullptr;
+  const bool fused_ln = ln_g != nullptr;
+  if (fused_ln) {
+    B200_CHECK_ARG(ntaps == 1 && nb == 1 && w == 1 && stride == 1 && ksplit <= 1 && !out_fp32 && c2 == 0 && !rowvec &&
+                   block_n % 64 == 0, "linear_ln: needs a plain bf16 linear layer");
+    cta_pair = 0;
+  }
   if (fused_lora) {
     B200_CHECK_ARG(ntaps == 1 && nb == 1 && w == 1 && stride == 1 && ksplit <= 1 && !geglu && !out_fp32 && c1 == 64 && !a1 &&
                    c2 == 0, "linear_lora: needs a plain linear layer with a 64-column LoRA segment");
+    B200_CHECK_ARG(!fused_ln || !t_out, "linear_ln: no global copy of T in the LayerNorm-fused form");
     B200_CHECK_ARG(2 * block_n + 64 <= 512, "linear_lora: block_n %d leaves no TMEM columns for T", block_n);
     cta_pair = 0;
   }
@@ -886,6 +993,21 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
     p.lora_kb = c0 / 64;
     p.m_rows = h;
     p.t_out = reinterpret_cast<__nv_bfloat16*>(t_out);
+  }
+  if (fused_ln) {
+    p.ln_stats = ln_stats;
+    p.ln_chunks = c0 / 64;
+    p.ln_c = c0;
+    p.ln_eps = ln_eps;
+    p.ln_g = ln_g; p.ln_ga = ln_ga; p.ln_ba = ln_ba;
+    p.m_rows = h;
+  }
+  if (stat_out) {
+    B200_CHECK_ARG(p.tma_out && ksplit <= 1 && !geglu && n_valid % 64 == 0 && !fused_ln,
+                   "conv_gemm: stat_out needs the plain bf16 TMA-store epilogue");
+    cta_pair = 0;
+    p.stat_out = stat_out;
+    p.stat_chunks = n_valid / 64;
   }
   int tc = 32;
   while (tc < 2 * block_n + p.lora_n) tc *= 2;
@@ -967,6 +1089,10 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
     cudaFuncSetAttribute(conv_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     cudaFuncSetAttribute(conv_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     cudaFuncSetAttribute(conv_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaFuncSetAttribute(conv_gemm_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaFuncSetAttribute(conv_gemm_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaFuncSetAttribute(conv_gemm_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaFuncSetAttribute(conv_gemm_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   }
   int grid = p.num_m_groups * p.num_n_tiles * p.ksplit;
   int cap = max_ctas > 0 ? max_ctas : num_sms;
@@ -977,7 +1103,19 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
                                                   stream, 2, tA[0], tA[1], tA[2], tB, tO, tLA, p));
   } else {
     if (grid > cap) grid = cap;
-    if (fused_lora)
+    if (stat_out && !fused_ln && fused_lora)
+      B200_CHECK_PDL("linear_stats(lora)", launch_pdl(conv_gemm_kernel<false, true, false, true>, dim3(grid), dim3(kThreads),
+                                                      (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+    else if (stat_out && !fused_ln)
+      B200_CHECK_PDL("linear_stats", launch_pdl(conv_gemm_kernel<false, false, false, true>, dim3(grid), dim3(kThreads),
+                                                (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+    else if (fused_lora && fused_ln)
+      B200_CHECK_PDL("linear_ln(lora)", launch_pdl(conv_gemm_kernel<false, true, true>, dim3(grid), dim3(kThreads),
+                                                   (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+    else if (fused_ln)
+      B200_CHECK_PDL("linear_ln", launch_pdl(conv_gemm_kernel<false, false, true>, dim3(grid), dim3(kThreads),
+                                             (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+    else if (fused_lora)
       B200_CHECK_PDL("linear_lora", launch_pdl(conv_gemm_kernel<false, true>, dim3(grid), dim3(kThreads), (size_t)smem_bytes,
                                                stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
     else

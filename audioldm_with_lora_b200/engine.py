@@ -150,6 +150,20 @@ class UNetEngine:
                                        num_sms=getattr(self, "_tiling_sms", ops.NUM_SMS), max_bn=max_bn)
         return packing.pack(segs, bias, bn, ntaps, c0, c1, c2, geglu, device=self.device, ksplit=ks)
 
+    def _ln_pack(self, w: Tensor, bias: Optional[Tensor], gamma: Tensor, beta: Tensor, m_tiles: int, c: int, *,
+                 geglu: bool = False, lora_seg: Optional[Tensor] = None, max_bn: int = 256) -> PackedWeight:
+        """Weights of a linear layer that consumes LayerNorm(x), with the LayerNorm folded in (b200_linear_ln):
+        rows gamma o W (+ the s.B K segment), bias' = W beta + bias, ln_g = column sums of the bf16-rounded rows."""
+        w = w.float()
+        wg = w * gamma.float()[None, :]
+        b2 = w @ beta.float() + (bias.float() if bias is not None else 0.0)
+        segs = [wg] + ([lora_seg] if lora_seg is not None else [])
+        pw = self._pw(segs, b2, m_tiles, 1, c, lora_seg.shape[1] if lora_seg is not None else 0, geglu=geglu,
+                      split=False, max_bn=max_bn)
+        pw.ln_g = pw.w[:, :c].float().sum(1).contiguous()
+        pw.lora_fused = lora_seg is not None
+        return pw
+
     def _build_plan(self, nb: int, h: int, w: int) -> dict:
         cfg, sd, g = self.cfg, self.sd, self.graph
         sizes = level_sizes(h, w, len(cfg.block_out_channels))
@@ -186,6 +200,9 @@ class UNetEngine:
             W[t.name + ".proj_in"] = self._pw([sd[t.name + ".proj_in.weight"][:, :, 0, 0]], sd[t.name + ".proj_in.bias"], mt, 1, c)
             W[t.name + ".proj_out"] = self._pw([sd[t.name + ".proj_out.weight"][:, :, 0, 0]], sd[t.name + ".proj_out.bias"], mt, 1, c)
             W[b + ".ff.net.0.proj"] = self._pw([sd[b + ".ff.net.0.proj.weight"]], sd[b + ".ff.net.0.proj.bias"], mt, 1, c, geglu=True)
+            if ops.LN_FUSED:          # norm3 folded into ff.net.0.proj (engine._Runner.tfm)
+                W[b + ".ff.net.0.proj.ln"] = self._ln_pack(sd[b + ".ff.net.0.proj.weight"], sd[b + ".ff.net.0.proj.bias"],
+                                                           sd[b + ".norm3.weight"], sd[b + ".norm3.bias"], mt, c, geglu=True)
             W[b + ".ff.net.2"] = self._pw([sd[b + ".ff.net.2.weight"]], sd[b + ".ff.net.2.bias"], mt, 1, 4 * c)
 
         lvl_of: Dict[str, int] = {}
@@ -259,6 +276,27 @@ class UNetEngine:
                 else:
                     W.pop(p + ".lora_down_qkv", None)
                     W[p + ".qkv"] = self._pw([wqkv], None, mt, 1, c)
+                # the same projection with norm1 / norm2 folded in (sampling path)
+                W.pop(p + ".qkv.ln", None); W.pop(p + ".lora_down_qkv.ln", None)
+                if ops.LN_FUSED:
+                    ln = "norm1" if a == "attn1" else "norm2"
+                    b_ = f"{t.name}.transformer_blocks.0"
+                    gamma, beta = sd[f"{b_}.{ln}.weight"].float(), sd[f"{b_}.{ln}.bias"].float()
+                    if any(e is not None for e in ents):
+                        if ops.LORA_FUSED and kp == 64:
+                            W[p + ".qkv.ln"] = self._ln_pack(wqkv, None, gamma, beta, mt, c, lora_seg=seg,
+                                                             max_bn=ops.LORA_FUSED_MAX_BN)
+                            W[p + ".qkv.ln"].alg_macs_per_row = float(3 * c * c + 2 * r_tot * c)
+                            down = packing.pack_lora_down([x * gamma[None, :] if x is not None else None for x in a_list], c,
+                                                          device=self.device)
+                            down.lora_rows = r_tot
+                            down.ln_g = down.w.float().sum(1).contiguous()
+                            ba = torch.zeros(64)
+                            ba[:r_tot] = torch.cat([x.float() for x in a_list if x is not None]) @ beta
+                            down.bias = ba.to(self.device)
+                            W[p + ".lora_down_qkv.ln"] = down
+                    else:
+                        W[p + ".qkv.ln"] = self._ln_pack(wqkv, None, gamma, beta, mt, c)
                 eo = self.lora.get(f"{p}.to_out.0")
                 wo, bo = sd[f"{p}.to_out.0.weight"], sd[f"{p}.to_out.0.bias"]
                 if eo is not None:
@@ -547,6 +585,25 @@ class _Runner:
         self.ar.release(ws)
         return out
 
+    def linear_ln(self, name, a0, stats, lvl, *, down=None, eps=1e-5):
+        pw = self.W[name]
+        out = self.ar.alloc((self.M(lvl), pw.n_valid), torch.bfloat16)
+        return ops.linear_ln(pw, a0, self.M(lvl), out, stats, eps=eps, down=down, max_ctas=self.max_ctas)
+
+    def linear_with_stats(self, name, a0, lvl, *, down=None, residual=None):
+        """A linear layer whose output feeds a LayerNorm-folded GEMM: (output, its per-row chunk statistics)."""
+        pw = self.W[name]
+        m = self.M(lvl)
+        out = self.ar.alloc((m, pw.n_valid), torch.bfloat16)
+        stats = self.ar.alloc((m, pw.n_valid // 64, 2), torch.float32)
+        T = None
+        use_down = down if (down is not None and ops.linear_lora_ok(pw, down)) else None
+        if down is not None and use_down is None:
+            T = self.linear(name.replace(".to_out", ".lora_down_o"), a0, lvl)
+        ops.linear_stats(pw, a0, m, out, stats, a1=T, down=use_down, residual=residual, max_ctas=self.max_ctas)
+        self.ar.release(T)
+        return out, stats
+
     def linear_lora(self, name, down, a0, lvl, *, residual=None):
         pw = self.W[name]
         out = self.ar.alloc((self.M(lvl), pw.n_valid), torch.bfloat16)
@@ -584,29 +641,58 @@ class _Runner:
     def tfm(self, t: TfmDesc, x, lvl):
         ar, S, W, M = self.ar, self.S, self.W, self.M(lvl)
         c = t.c
+        hh, ww = self.sizes[lvl]
         b = t.name + ".transformer_blocks.0"
+
+        def foreign(p_):
+            return bool(self.attn_overrides and p_ in self.attn_overrides)
+
+        def fused(p_):          # norm folded into this attention's QKV GEMM?  (its input's producer must be one of ours)
+            prev_ok = not foreign(b + ".attn1") if p_.endswith("attn2") else W[t.name + ".proj_in"].ksplit == 1
+            return p_ + ".qkv.ln" in W and not foreign(p_) and prev_ok and W[p_ + ".to_out"].ksplit == 1 and c % 64 == 0
+
+        ff_fused = b + ".ff.net.0.proj.ln" in W and not foreign(b + ".attn2") and W[b + ".attn2.to_out"].ksplit == 1 \
+            and c % 64 == 0
         n0 = self.gn(x, c, None, 0, lvl, t.name + ".norm", 1e-6, False)
-        tok = self.linear(t.name + ".proj_in", n0, lvl)
+        # every producer of the token stream leaves the row statistics its consumer's folded LayerNorm needs
+        stats = None
+        if fused(b + ".attn1"):
+            tok, stats = self.linear_with_stats(t.name + ".proj_in", n0, lvl)
+        else:
+            tok = self.linear(t.name + ".proj_in", n0, lvl)
         ar.release(n0)
-        for a, ln_name in (("attn1", "norm1"), ("attn2", "norm2")):
+        order = (("attn1", "norm1"), ("attn2", "norm2"))
+        for i, (a, ln_name) in enumerate(order):
             p = f"{b}.{a}"
-            ln = ar.alloc((M, c), torch.bfloat16)
-            ops.layernorm(tok, M, c, S[f"{b}.{ln_name}.weight"], S[f"{b}.{ln_name}.bias"], 1e-5, ln)
-            if self.attn_overrides and p in self.attn_overrides:
-                # foreign attention processor installed through the diffusers seam: hand it the
-                # LayerNorm output as a torch tensor, add its result to the residual stream.
-                # (torch glue on purpose: this is not the B200 path.)
-                hh, ww = self.sizes[lvl]
-                res = self.attn_overrides[p](ln.view(self.nb, hh * ww, c))
-                new_tok = ar.alloc((M, c), torch.bfloat16)
-                new_tok.copy_((tok.float() + res.reshape(M, c).float()).to(torch.bfloat16))
-                ar.release(ln); ar.release(tok)
-                tok = new_tok
-                continue
-            ao = self.attention(p, ln, lvl, c)
-            ar.release(ln)
+            next_fused = fused(f"{b}.attn2") if i == 0 else ff_fused
+            ln = None
+            if stats is not None:
+                # LayerNorm folded into the QKV GEMM (and the q/k/v LoRA down-projection computed inside it)
+                qkv = self.linear_ln(p + ".qkv.ln", tok, stats, lvl, down=W.get(p + ".lora_down_qkv.ln"))
+                ar.release(stats)
+                stats = None
+                ao = ar.alloc((M, c), torch.bfloat16)
+                ops.attention(qkv, ao, self.nb, hh * ww, self.cfg.heads, c // self.cfg.heads, variant=self.eng.attn_variant)
+                ar.release(qkv)
+            else:
+                ln = ar.alloc((M, c), torch.bfloat16)
+                ops.layernorm(tok, M, c, S[f"{b}.{ln_name}.weight"], S[f"{b}.{ln_name}.bias"], 1e-5, ln)
+                if self.attn_overrides and p in self.attn_overrides:
+                    # foreign attention processor installed through the diffusers seam: hand it the
+                    # LayerNorm output as a torch tensor, add its result to the residual stream.
+                    # (torch glue on purpose: this is not the B200 path.)
+                    res = self.attn_overrides[p](ln.view(self.nb, hh * ww, c))
+                    new_tok = ar.alloc((M, c), torch.bfloat16)
+                    new_tok.copy_((tok.float() + res.reshape(M, c).float()).to(torch.bfloat16))
+                    ar.release(ln); ar.release(tok)
+                    tok = new_tok
+                    continue
+                ao = self.attention(p, ln, lvl, c)
+                ar.release(ln)
             down_o = W.get(p + ".lora_down_o")
-            if ops.linear_lora_ok(W[p + ".to_out"], down_o):
+            if next_fused:
+                new_tok, stats = self.linear_with_stats(p + ".to_out", ao, lvl, down=down_o, residual=tok)
+            elif ops.linear_lora_ok(W[p + ".to_out"], down_o):
                 new_tok = self.linear_lora(p + ".to_out", down_o, ao, lvl, residual=tok)
             else:
                 To = self.linear(p + ".lora_down_o", ao, lvl) if down_o is not None else None
@@ -614,10 +700,14 @@ class _Runner:
                 ar.release(To)
             ar.release(ao); ar.release(tok)
             tok = new_tok
-        ln = ar.alloc((M, c), torch.bfloat16)
-        ops.layernorm(tok, M, c, S[b + ".norm3.weight"], S[b + ".norm3.bias"], 1e-5, ln)
-        ffh = self.linear(b + ".ff.net.0.proj", ln, lvl)
-        ar.release(ln)
+        if stats is not None:
+            ffh = self.linear_ln(b + ".ff.net.0.proj.ln", tok, stats, lvl)      # norm3 folded in, GEGLU in the same epilogue
+            ar.release(stats)
+        else:
+            ln = ar.alloc((M, c), torch.bfloat16)
+            ops.layernorm(tok, M, c, S[b + ".norm3.weight"], S[b + ".norm3.bias"], 1e-5, ln)
+            ffh = self.linear(b + ".ff.net.0.proj", ln, lvl)
+            ar.release(ln)
         new_tok = self.linear(b + ".ff.net.2", ffh, lvl, residual=tok)
         ar.release(ffh); ar.release(tok)
         out = self.linear(t.name + ".proj_out", new_tok, lvl, residual=x)

@@ -185,6 +185,51 @@ def linear_lora(pw: PackedWeight, down: PackedWeight, x: Tensor, m: int, out: Te
     return out
 
 
+# LayerNorm folded into the consuming GEMM (b200_linear_ln + b200_linear_stats).  Correct and tested, removes 48 launches
+# per step, but measured on B200 it does not pay yet: 5.36 vs 5.25 ms per step (the folded level-1 QKV GEMM needs
+# 192-wide tiles for the in-kernel LoRA branch and loses more than the LayerNorm launch cost).  Opt-in.
+LN_FUSED = os.environ.get("B200_LN_FUSED", "0") != "0"
+
+
+def linear_stats(pw: PackedWeight, x: Tensor, m: int, out: Tensor, stat_out: Tensor, *, a1: Optional[Tensor] = None,
+                 down: Optional[PackedWeight] = None, residual: Optional[Tensor] = None, max_ctas: int = 0) -> Tensor:
+    """A linear layer that also leaves its output's per-row, per-64-column (sum, sum of squares) in stat_out
+    [m, n_valid / 64, 2] for a following LayerNorm-folded GEMM; see include/b200ldm.h::b200_linear_stats."""
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() == m * pw.c0 and out.dtype == torch.bfloat16
+    assert stat_out.dtype == torch.float32 and stat_out.numel() == m * (pw.n_valid // 64) * 2 and pw.n_valid % 64 == 0
+    assert pw.ksplit == 1 and not pw.geglu and pw.ntaps == 1
+    res_ld = pw.n_valid if residual is not None else 0
+    info = None
+    if _lib.PROFILE is not None:
+        info = {"flops": 2.0 * m * pw.macs_per_row, "m": m, "n": pw.n_valid, "k": pw.k, "bn": pw.block_n, "taps": 1,
+                "desc": "stats" + ("+lora" if down is not None else "")}
+    call("b200_linear_stats", ptr(x), pw.c0, ptr(a1) if (pw.c1 and down is None) else None, pw.c1, m, ptr(pw.w), pw.n_pad,
+         pw.n_valid, ptr(pw.bias), ptr(residual), res_ld, ptr(out), pw.n_valid, pw.block_n, max_ctas,
+         ptr(down.w) if down is not None else None, down.lora_rows if down is not None else 0, ptr(stat_out), stream(),
+         info=info)
+    return out
+
+
+def linear_ln(pw: PackedWeight, x: Tensor, m: int, out: Tensor, stats: Tensor, *, eps: float = 1e-5,
+              down: Optional[PackedWeight] = None, residual: Optional[Tensor] = None, max_ctas: int = 0) -> Tensor:
+    """out = LN(x) W^T (+ LoRA) with the LayerNorm folded into the GEMM; pw / down are `.ln`-packed (gamma folded in,
+    pw.ln_g / down.ln_g / down.bias set); see include/b200ldm.h::b200_linear_ln."""
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() == m * pw.c0 and out.dtype == torch.bfloat16
+    assert pw.bias is not None and getattr(pw, "ln_g", None) is not None and pw.ksplit == 1
+    assert (pw.c1 == 64) == (down is not None)
+    assert stats.dtype == torch.float32 and stats.numel() == m * (pw.c0 // 64) * 2
+    res_ld = pw.n_valid if residual is not None else 0
+    info = None
+    if _lib.PROFILE is not None:
+        info = {"flops": 2.0 * m * pw.macs_per_row, "m": m, "n": pw.n_valid, "k": pw.k, "bn": pw.block_n, "taps": 1,
+                "desc": "ln-fused" + ("+lora" if down is not None else "") + ("+geglu" if pw.geglu else "")}
+    call("b200_linear_ln", ptr(x), pw.c0, m, ptr(pw.w), pw.n_pad, pw.n_valid, ptr(pw.bias), ptr(pw.ln_g), float(eps),
+         ptr(stats), ptr(residual), res_ld, ptr(out), pw.n_valid, int(pw.geglu), pw.block_n, max_ctas,
+         ptr(down.w) if down is not None else None, down.lora_rows if down is not None else 0,
+         ptr(down.ln_g) if down is not None else None, ptr(down.bias) if down is not None else None, stream(), info=info)
+    return out
+
+
 def set_sm_budget(n: int) -> None:
     """Launch-shape hint for the following launches of this thread (0 = the whole GPU); see b200_set_sm_budget."""
     _lib.check(_lib.load().b200_set_sm_budget(int(n)), "b200_set_sm_budget")

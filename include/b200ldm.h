@@ -65,6 +65,26 @@ int b200_linear_lora(const void* x, int c, int m, const void* wpacked, int n_pad
                      const void* residual, int res_ld, void* out, int out_ld, int block_n, int max_ctas,
                      const void* lora_down, int lora_rows, void* t_out, void* stream);
 
+/* Linear layer consuming LayerNorm(x) with the LayerNorm folded into the GEMM (BasicTransformerBlock norm1/2/3 ->
+ * attn.to_q/k/v, ff.net.0.proj; diffusers via train_audioldm_lora.py:539-546), optionally with the in-kernel LoRA branch
+ * and the GEGLU epilogue:   out = LN(x) W^T (+ (LN(x) A^T)(s B)^T) (+ residual).
+ * The GEMM runs on the raw rows x with gamma folded into the packed weights (wpacked = [gamma o W | s.B]); the epilogue
+ * finishes the normalisation per row:  LN(x) W^T = rstd (x (gamma o W)^T - mu ln_g) + bias,  ln_g[n] = sum_c gamma_c W[n,c],
+ * bias[n] = sum_c beta_c W[n,c] (+ the layer's own bias); (mu, rstd) of a row come from ln_stats fp32 [m, c / 64, 2], the
+ * per-chunk (sum, sum of squares) that the kernel which produced x left behind (b200_linear_stats).  With LoRA: lora_down = gamma o A stacked [64, c], ln_ga / ln_ba fp32 [64].
+ * Removes the LayerNorm launch and the normalised activation's round trip through HBM. */
+int b200_linear_ln(const void* x, int c, int m, const void* wpacked, int n_pad, int n_valid, const float* bias,
+                   const float* ln_g, float ln_eps, const float* ln_stats, const void* residual, int res_ld, void* out,
+                   int out_ld, int geglu, int block_n, int max_ctas, const void* lora_down, int lora_rows,
+                   const float* ln_ga, const float* ln_ba, void* stream);
+
+/* Producer side of that fusion: a linear layer [m, c] -> [m, n] (optional K segment a1 / c1, or the in-kernel LoRA
+ * branch) whose epilogue also writes stat_out fp32 [m, n_valid / 64, 2]: per row and 64-column chunk the (sum, sum of
+ * squares) of the bf16 values it stores -- fixed slots, no atomics.  b200_linear_ln reads them as ln_stats. */
+int b200_linear_stats(const void* x, int c, const void* a1, int c1, int m, const void* wpacked, int n_pad, int n_valid,
+                      const float* bias, const void* residual, int res_ld, void* out, int out_ld, int block_n,
+                      int max_ctas, const void* lora_down, int lora_rows, float* stat_out, void* stream);
+
 /* Launch-shape hint for the calling thread: the number of SMs the following launches should size themselves for
  * (0 = all).  Used when independent sub-batch chains run concurrently on parallel streams. */
 int b200_set_sm_budget(int n);

@@ -58,6 +58,43 @@ def set_sm_budget(n):
     pass
 
 
+def linear_stats(pw, x, m, out, stat_out, *, a1=None, down=None, residual=None, max_ctas=0):
+    if down is not None:
+        linear_lora(pw, down, x, m, out, residual=residual)
+    else:
+        conv_gemm(pw, x, 1, m, 1, out, a1=a1, residual=residual)
+    o = out.view(m, pw.n_valid // 64, 64).float()
+    st = stat_out.view(m, pw.n_valid // 64, 2)
+    st[..., 0] = o.sum(-1)
+    st[..., 1] = (o * o).sum(-1)
+    return out
+
+
+def linear_ln(pw, x, m, out, stats, *, eps=1e-5, down=None, residual=None, max_ctas=0):
+    """Emulates the kernel's algebra (raw x through gamma-folded weights, per-row correction in the epilogue, row
+    statistics from the producer's per-chunk partial sums)."""
+    c = pw.c0
+    xf = x.view(m, c).float()
+    st = stats.view(m, c // 64, 2).sum(1)
+    mu = (st[:, 0] / c)[:, None]
+    rs = ((st[:, 1] / c)[:, None] - mu * mu).clamp_min(0).add(eps).rsqrt()
+    acc = xf @ pw.w[:, :c].float().T
+    if down is not None:
+        r = down.lora_rows
+        t = xf @ down.w[:r].float().T - mu * down.ln_g[:r] + down.bias[:r] / rs
+        T = torch.zeros(m, 64); T[:, :r] = t
+        acc = acc + T.to(bf16).float() @ pw.w[:, c:c + 64].float().T
+    acc = (acc - mu * pw.ln_g) * rs + pw.bias
+    if pw.geglu:
+        tt = acc.view(m, -1, 2, pw.block_n // 2)
+        acc = (tt[:, :, 0] * F.gelu(tt[:, :, 1])).reshape(m, -1)
+    acc = acc[:, :pw.n_valid]
+    if residual is not None:
+        acc = acc + residual.reshape(m, -1)[:, :pw.n_valid].float()
+    _store(out, acc, pw.n_valid)
+    return out
+
+
 def linear_lora_ok(pw, down):
     return (getattr(pw, "lora_fused", False) and down is not None and getattr(down, "lora_rows", 0) > 0 and pw.c1 == 64 and
             pw.c2 == 0 and pw.ntaps == 1 and not pw.geglu and pw.ksplit == 1 and pw.block_n <= 192)
@@ -346,5 +383,5 @@ def install(monkeypatch, ops_module):
     """Replace the kernel wrappers of `ops_module` (keeps PackedWeight / tiling helpers)."""
     for name in ("conv_gemm", "groupnorm_silu", "layernorm", "attention", "time_class_embed",
                  "pack_nchw_to_nhwc", "unpack_nhwc_to_nchw", "upsample_nearest", "sampler_step", "add_noise",
-                 "adamw_flat", "mse_partial", "set_sm_budget", "linear_lora_ok", "linear_lora") + TRAIN_OPS:
+                 "adamw_flat", "mse_partial", "set_sm_budget", "linear_lora_ok", "linear_lora", "linear_ln", "linear_stats") + TRAIN_OPS:
         monkeypatch.setattr(ops_module, name, globals()[name])
