@@ -362,7 +362,10 @@ def main():
                             "except the LoRA-adapted projections, which run in b200_linear_lora) / sum of their per-launch "
                             "device times (each launch replayed 8x in its own CUDA graph, CUDA events on the launching stream)",
                      "launches_per_step": cg["calls"], "ms_per_step": cg["ms"], "share_of_step": cg["ms"] / total_ms,
-                     "traffic": traffic,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE profiled launch of this kernel (ncu --set full);
+                     # which launch, its algorithmic bytes and the other counters are in traffic_detail
+                     "traffic": (traffic["dram_bytes_read"] + traffic["dram_bytes_write"]) if traffic else None,
+                     "traffic_detail": traffic,
                      "whole_step": {"achieved": unet_flops / (unet_step_ms / 1e3) / 1e12, "frac": unet_flops / (unet_step_ms / 1e3) / 1e12 / sustained}},
         "kernel_breakdown_ms": {k: {"ms": round(v["ms"], 4), "calls": v["calls"],
                                     "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["flops"] and v["ms"] else None}
