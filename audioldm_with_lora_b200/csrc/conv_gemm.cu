@@ -31,9 +31,6 @@
 #include "ptx.cuh"
 
 // Build-time variants (A/B-tested on B200; defaults are the faster ones):
-#ifndef B200_EPI_V3
-#define B200_EPI_V3 0            // 1: bias/rowvec via a per-warp smem vector + residual prefetched into registers
-#endif
 #ifndef B200_GEMM_PROFILE
 #define B200_GEMM_PROFILE 0      // 1: CTA-0 cycle timeline + MMA-thread cost breakdown (B200_GEMM_DEBUG & 4 / & 8)
 #endif
@@ -53,7 +50,7 @@ static constexpr int kEpiWarps = 8;
 static constexpr int kProducerBWarp = 2 + kEpiWarps;    // only with B200_SPLIT_PRODUCERS
 static constexpr int kThreads = 64 + kEpiWarps * 32 + (B200_SPLIT_PRODUCERS ? 32 : 0);   // warp0 TMA, warp1 MMA, warps2-9 epilogue
 static constexpr int kEpiStageBytes = 32 * 128;         // per-warp staging: 32 rows x 64 bf16
-static constexpr int kEpiVecBytes = 128 * 4;            // per-warp bias(+rowvec) vector of the current chunk
+static constexpr int kEpiVecBytes = 128 * 4;            // per-warp scratch (row statistics of the LayerNorm-folded form)
 static constexpr int kSmemLimit = 227 * 1024;
 
 struct ConvGemmParams {
@@ -163,7 +160,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int stage_bytes = kABytes + b_rows * kBlockK * 2;
   uint8_t* t_tile = smem + p.stages * stage_bytes;                 // [128 rows][64 bf16], 128B-swizzled (fused LoRA only)
   uint8_t* epi_smem = t_tile + (kLora ? kABytes : 0);
-  float* epi_vec = reinterpret_cast<float*>(epi_smem + kEpiWarps * kEpiStageBytes);
+  [[maybe_unused]] float* epi_vec = reinterpret_cast<float*>(epi_smem + kEpiWarps * kEpiStageBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * (kEpiStageBytes + kEpiVecBytes));
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;
@@ -440,8 +437,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const uint32_t stage_row = smem_u32(stage) + lane * 128;
     const int half = p.block_n / 2;
     const int out_cols = p.geglu ? half : p.block_n;     // output columns per tile
-    [[maybe_unused]] float* my_vec = epi_vec + (warp - 2) * (kEpiVecBytes / 4);
-    [[maybe_unused]] const bool rv_uniform = p.W * p.BH >= 32;            // the warp's 32 rows lie in one image
     int it = 0;
     for (int t = tile0; t < num_tiles; t += tile_step, ++it) {
       const int buf = it & 1;
@@ -454,7 +449,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int n_t = (m_tile / p.tiles_h) * p.BNI;
       const int h = h_t + hl;
       const int n = n_t + nl;
-      [[maybe_unused]] const int n_warp = n_t + q_n;                        // image of the warp's rows (when rv_uniform)
       bool row_ok = (h < p.H) && (n < p.NB);
       size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + wl;
       if (p.stride == 2) {
@@ -463,37 +457,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * p.block_n;
       const int nchunks = p.tma_out ? (out_cols >> 6) : 0;
-#if B200_EPI_V3
-      // Per-chunk additive vector (bias + this image's embedding row) goes through a per-warp smem buffer and
-      // the residual row segment through registers; both are fetched BEFORE the accumulator is waited for.
-      float2 vec_a = make_float2(0.f, 0.f), vec_b = make_float2(0.f, 0.f);
-      uint4 res[8];
-      auto prefetch = [&](int cc) {
-        const int gcol = n_tile * out_cols + cc * 64 + 2 * lane;          // this lane's two columns of the chunk
-        vec_a = make_float2(0.f, 0.f);
-        vec_b = make_float2(0.f, 0.f);
-        if (!p.geglu) {
-          if (p.bias) vec_a = *reinterpret_cast<const float2*>(p.bias + gcol);
-          if (p.rowvec && rv_uniform && gcol < p.n_valid && n_warp < p.NB) {
-            const float2 rv = *reinterpret_cast<const float2*>(p.rowvec + static_cast<size_t>(n_warp) * p.rowvec_ld + gcol);
-            vec_a.x += rv.x;
-            vec_a.y += rv.y;
-          }
-        } else if (p.bias) {
-          const int bcol = n_tile * p.block_n + cc * 64 + 2 * lane;
-          vec_a = *reinterpret_cast<const float2*>(p.bias + bcol);
-          vec_b = *reinterpret_cast<const float2*>(p.bias + bcol + half);
-        }
-        if (p.residual && row_ok) {
-          const __nv_bfloat16* rp = p.residual + pix * p.res_ld + n_tile * out_cols + cc * 64;
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            res[g] = (n_tile * out_cols + cc * 64 + g * 8 < p.n_valid) ? *reinterpret_cast<const uint4*>(rp + g * 8)
-                                                                        : make_uint4(0, 0, 0, 0);
-        }
-      };
-      if (hf < nchunks) prefetch(hf);
-#endif
       [[maybe_unused]] float ln_mu = 0.f, ln_rs = 0.f;
       if (kLn) {
         // ---- LayerNorm statistics of this thread's row: the producer of x left per-chunk partial sums (fixed order)
@@ -564,86 +527,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tc_fence_after();
 
       if (p.tma_out) {
-#if B200_EPI_V3
-        // -------- bf16, stride 1: 64-column chunks -> swizzled smem -> TMA store
-        for (int cc = hf; cc < nchunks; cc += 2) {
-          __syncwarp();                                     // previous chunk's readers of my_vec are done
-          *reinterpret_cast<float2*>(my_vec + 2 * lane) = vec_a;
-          if (p.geglu) *reinterpret_cast<float2*>(my_vec + 64 + 2 * lane) = vec_b;
-          __syncwarp();
-          uint32_t pk[32];
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int oc = cc * 64 + hh * 32;              // output column inside the tile
-            const int gcol = n_tile * out_cols + oc;       // global output column
-            uint32_t r[32];
-            if (!p.geglu) {
-              tmem_ld_x32(t_row + oc, r);
-              tmem_wait_ld();
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-                add8(v, my_vec + hh * 32 + g * 8);
-                const int cg = gcol + g * 8;
-                if (row_ok && cg < p.n_valid) {
-                  if (p.rowvec && !rv_uniform) add8(v, p.rowvec + static_cast<size_t>(n) * p.rowvec_ld + cg);
-                  if (p.residual) {
-                    const uint4 rr = res[hh * 4 + g];
-                    v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
-                    v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
-                  }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pk[hh * 16 + g * 4 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-              }
-            } else {
-              // GEGLU: tile columns [0, bn/2) are values, [bn/2, bn) the matching gates.
-              uint32_t rg[32];
-              tmem_ld_x32(t_row + oc, r);
-              tmem_ld_x32(t_row + half + oc, rg);
-              tmem_wait_ld();
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float v[8], gt[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  v[j] = __uint_as_float(r[g * 8 + j]);
-                  gt[j] = __uint_as_float(rg[g * 8 + j]);
-                }
-                add8(v, my_vec + hh * 32 + g * 8);
-                add8(gt, my_vec + 64 + hh * 32 + g * 8);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] *= gelu_erf(gt[j]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pk[hh * 16 + g * 4 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-              }
-            }
-          }
-          if (cc + 2 < nchunks) prefetch(cc + 2);          // next chunk's vector / residual while this one is stored
-          if (warp == 2 && lane == 0) TL(cc == 0 ? 16 : 20);
-          // the previous TMA store of this warp must have finished reading the staging tile
-          if (lane == 0) tma_store_wait_read<0>();
-          __syncwarp();
-          if (warp == 2 && lane == 0) TL(cc == 0 ? 17 : 21);
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const uint32_t addr = stage_row + ((g ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
-                         "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3])
-                         : "memory");
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (warp == 2 && lane == 0) TL(cc == 0 ? 18 : 22);
-          if (lane == 0) {
-            tma_store_4d(&tmOut, stage, n_tile * out_cols + cc * 64, q_w, h_t + q_h, n_t + q_n);
-            tma_store_commit();
-          }
-          if (warp == 2 && lane == 0) TL(cc == 0 ? 19 : 23);
-        }
-#else
         // -------- bf16, stride 1: 64-column chunks -> swizzled smem -> TMA store
         for (int cc = hf; cc < nchunks; cc += 2) {
           uint32_t pk[32];
@@ -733,7 +616,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             tma_store_commit();
           }
         }
-#endif
       } else {
         // -------- fp32 output and/or stride 2: direct 16-byte stores, 32-column groups
         const int col_base = n_tile * p.block_n;
