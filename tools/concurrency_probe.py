@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Do two independent chains of small dependent GEMMs overlap inside one CUDA graph?  (why engine.forward_branched does not pay)"""
+"""Do two independent chains of small dependent GEMMs overlap inside one CUDA graph?  (the premise of engine.forward_nhwc(mid_branches=k))"""
 import sys
 from pathlib import Path
 import torch
