@@ -37,9 +37,6 @@
 #ifndef B200_B_EARLY
 #define B200_B_EARLY 1           // 1: the weight producer does not wait for the previous grid (see the PDL note in the kernel)
 #endif
-#ifndef B200_SPLIT_PRODUCERS
-#define B200_SPLIT_PRODUCERS 1   // 1: activation (A) and weight (B) TMA streams issued by two different warps
-#endif
 
 namespace b200 {
 
@@ -47,8 +44,8 @@ static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;              // 64 bf16 = one 128B swizzle row
 static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 static constexpr int kEpiWarps = 8;
-static constexpr int kProducerBWarp = 2 + kEpiWarps;    // only with B200_SPLIT_PRODUCERS
-static constexpr int kThreads = 64 + kEpiWarps * 32 + (B200_SPLIT_PRODUCERS ? 32 : 0);   // warp0 TMA, warp1 MMA, warps2-9 epilogue
+static constexpr int kProducerBWarp = 2 + kEpiWarps;    // the weight (B) TMA stream has its own warp
+static constexpr int kThreads = 64 + kEpiWarps * 32 + 32;   // warp0 TMA (A), warp1 MMA, warps2-9 epilogue, warp10 TMA (B)
 static constexpr int kEpiStageBytes = 32 * 128;         // per-warp staging: 32 rows x 64 bf16
 static constexpr int kEpiVecBytes = 128 * 4;            // per-warp scratch (row statistics of the LayerNorm-folded form)
 static constexpr int kSmemLimit = 227 * 1024;
@@ -80,8 +77,8 @@ struct ConvGemmParams {
   int kb_per_split;
   size_t split_stride;              // elements between the partial-sum planes
   int a_rank2;                      // linear layers (W = 1, one image): A tensor maps are plain 2-D [rows, K]
-  int debug;                        // profiling knobs (env B200_GEMM_DEBUG): 1 = no TMA after the first fill of each
-                                    // stage, 2 = no MMA (results are garbage; timing experiments only)
+  int debug;                        // profiling knobs (env B200_GEMM_DEBUG, -DB200_GEMM_PROFILE=1 builds only): 2 = no MMAs
+                                    // (results are garbage), 4 = CTA-0 timeline, 8 = per-k-block time stamps
   // Fused LoRA down-projection (linear layers, 1-CTA mode): phase 0 of every tile computes T = x . A^T (N = lora_n) on the
   // tensor core into TMEM columns [2 block_n, 2 block_n + lora_n); the epilogue warps turn it into a bf16 K-major
   // shared-memory tile while the base k-blocks run; the LoRA k-block (segment 1) then takes that tile as its A operand.
@@ -120,14 +117,20 @@ __device__ __forceinline__ float gelu_erf(float g) {
 }
 
 // debug timeline (B200_GEMM_DEBUG & 4): SM cycle counter of CTA 0 at fixed points of the kernel
-__device__ unsigned long long g_timeline[32];
+__device__ unsigned long long g_timeline[160];
 #if B200_GEMM_PROFILE
 #define TL(i)                                                        \
   do {                                                               \
-    if ((p.debug & 4) && blockIdx.x == 0) g_timeline[i] = clock64(); \
+    if ((p.debug & 4) && blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_timeline[i] = clock64(); \
+  } while (0)
+// per-k-block time stamps of CTA 0's first tile (B200_GEMM_DEBUG & 8): slot base + k-block
+#define PKB(base, k)                                                                               \
+  do {                                                                                             \
+    if ((p.debug & 8) && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && t == tile0 && (k) < 32) g_timeline[(base) + (k)] = clock64(); \
   } while (0)
 #else
 #define TL(i) do {} while (0)
+#define PKB(base, k) do {} while (0)
 #endif
 
 __device__ __forceinline__ void add8(float (&v)[8], const float* src) {
@@ -181,7 +184,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmB);
     if (p.tma_out) tma_prefetch_desc(&tmOut);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], B200_SPLIT_PRODUCERS ? 2 : 1);   // one arrive.expect_tx per producer thread
+      mbar_init(&full_bar[s], 2);    // one arrive.expect_tx per producer thread
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -212,122 +215,183 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // weight (B) producer: weights are never written inside a step, so with split producers its TMA stream starts
   // before the previous grid has drained (hides the HBM latency of the first weight tiles; B200_B_EARLY=0 disables).
   pdl_launch_dependents();
-  if (!(B200_SPLIT_PRODUCERS && B200_B_EARLY && warp == kProducerBWarp)) pdl_wait();
-  if (threadIdx.x == 0) TL(2);
+  if (warp != 0 && !(B200_B_EARLY && warp == kProducerBWarp)) pdl_wait();   // warp 0 (A producer): after its index math
 
-  if (warp == 0 || (B200_SPLIT_PRODUCERS && warp == kProducerBWarp)) {
-    // ================================================================ TMA producer (one thread per stream)
-    // A single-thread scalar loop, i.e. every instruction costs its full latency: k-block coordinates advance
-    // incrementally (no divisions) and the poll of the NEXT stage's empty barrier is issued before the current
-    // stage's TMA so that its latency is hidden.  (Splitting A and B over two warps was measured: no gain.)
-    if (lane == 0) {
-      const bool do_a = !B200_SPLIT_PRODUCERS || warp == 0;
-      const bool do_b = !B200_SPLIT_PRODUCERS || warp != 0;
-      const uint32_t my_bytes = ((do_a ? static_cast<uint32_t>(kABytes) : 0u) + (do_b ? static_cast<uint32_t>(stage_bytes - kABytes) : 0u)) *
-                                (kCta2 ? 2u : 1u);       // 2-CTA: the leader's barrier expects the pair's bytes
+  if (warp == 0) {
+    // ================================================================ activation (A) TMA producer
+    // One warp's instruction stream is serial: every instruction costs its full latency, and at 128-wide tiles the
+    // tensor pipe wants a k-block every 256 cycles.  So the loop body is kept minimal: the whole warp runs it with
+    // warp-uniform control flow (coordinates and addresses in uniform registers, one elected lane issues: no
+    // ELECT + R2UR.BROADCAST waterfall per TMA), 32-bit shared-window addresses advanced incrementally, the (segment,
+    // tap, channel-block) walk as nested loops instead of a per-k-block state machine, the watchdog out of line.
+    {
+      const bool lead = elect_one();
+      const int stages = p.stages, cb0 = p.cb0;
+      const int seg_end0 = p.seg_end0, seg_end1 = p.seg_end1;
+      const uint32_t stage_b = stage_bytes;
+      const uint32_t smem_a = smem_u32(smem), full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+      const uint32_t ring_end = smem_a + stages * stage_b;
+      const uint32_t a_bytes = static_cast<uint32_t>(kABytes) * (kCta2 ? 2u : 1u);   // 2-CTA: the leader's barrier expects the pair's bytes
       const bool expect = !kCta2 || cta_rank == 0;
-      int s = 0;
-      uint32_t ph = 0;
-      int fills = 0;
+      uint32_t slot = smem_a, bar_off = 0, ph = 0;
+      uint32_t d, fb;
+      // next ring slot: wait until the MMAs that read it have retired (a fresh barrier passes at once)
+      auto acquire = [&]() {
+        mbar_wait(empty_a + bar_off, ph ^ 1);
+        d = slot;
+        fb = full_a + bar_off;
+        slot += stage_b;
+        bar_off += 8;
+        if (slot == ring_end) { slot = smem_a; bar_off = 0; ph ^= 1; }
+      };
       for (int t = tile0; t < num_tiles; t += tile_step) {
-        const int n_tile = t % p.num_n_tiles;
-        const int m_group = (t / p.num_n_tiles) % p.num_m_groups;
+        // tile -> (n_tile, m_group, split); integer divisions cost ~150 cycles each in this lone thread: skip the trivial ones
+        const int tn = p.num_n_tiles == 1 ? t : t / p.num_n_tiles;
+        const int split = p.ksplit == 1 ? 0 : tn / p.num_m_groups;
+        const int m_group = tn - split * p.num_m_groups;
         const int m_tile = kCta2 ? 2 * m_group + static_cast<int>(cta_rank) : m_group;   // may be a phantom tile: all OOB
-        const int split = t / (p.num_n_tiles * p.num_m_groups);
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
-        const int h0 = (m_tile % p.tiles_h) * p.BH;
-        const int n0 = (m_tile / p.tiles_h) * p.BNI;
-        const int b_row0 = n_tile * p.block_n + static_cast<int>(cta_rank) * b_rows;
-        // incremental (segment, tap, channel-block) state of k-block kb_begin
-        int seg = kb_begin < p.seg_end0 ? 0 : (kb_begin < p.seg_end1 ? 1 : 2);
-        int tap = 0, cb = 0;
-        if (seg == 0) { tap = kb_begin / p.cb0; cb = kb_begin - tap * p.cb0; }
-        else cb = kb_begin - (seg == 1 ? p.seg_end0 : p.seg_end1);
-        int dh = 0, dw = 0;
-        if (seg == 0 && p.ntaps == 9) { dh = tap / 3 - 1; dw = tap - (tap / 3) * 3 - 1; }
+        const int n_img = p.tiles_h == 1 ? m_tile : m_tile / p.tiles_h;
+        const int h0 = (m_tile - n_img * p.tiles_h) * p.BH;
+        const int n0 = n_img * p.BNI;
+        int kb = kb_begin;
+        int cb = 0, dh = 0, dw = 0;
+        if (p.ntaps == 9) { dh = -1; dw = -1; }
+        if (kb > 0 && kb < seg_end0) {
+          const int tap = kb / cb0;
+          cb = kb - tap * cb0;
+          if (p.ntaps == 9) { dh = tap / 3 - 1; dw = tap - (tap / 3) * 3 - 1; }
+        }
+        // PDL: the activations are the previous kernel's output (the index math above overlapped its tail)
+        if (t == tile0) { pdl_wait(); TL(2); }
         if (kLora) {
-          // ---- phase 0: the tile's activations (A slot) and the stacked lora_A rows (B slot), c0 / 64 k-blocks
-          const uint32_t bytes0 = do_a ? static_cast<uint32_t>(kABytes) : static_cast<uint32_t>(p.lora_n) * kBlockK * 2;
-          for (int kb = 0; kb < p.lora_kb; ++kb) {
-            if (fills >= p.stages) mbar_wait(&empty_bar[s], ph ^ 1);
-            uint8_t* dst = smem + s * stage_bytes;
-            uint64_t* fb = &full_bar[s];
-            ++fills;
-            if (do_a && do_b) {
-              mbar_expect_tx(fb, static_cast<uint32_t>(kABytes) + static_cast<uint32_t>(p.lora_n) * kBlockK * 2);
-              tma_load_4d(dst, &tmA0, fb, kb * kBlockK, 0, h0, n0);
-              tma_load_2d(dst + kABytes, &tmLA, fb, kb * kBlockK, 0);
-            } else {
-              mbar_expect_tx(fb, bytes0);
-              if (do_a) tma_load_4d(dst, &tmA0, fb, kb * kBlockK, 0, h0, n0);
-              else tma_load_2d(dst + kABytes, &tmLA, fb, kb * kBlockK, 0);
+          // ---- phase 0: the tile's activations once more, against the stacked lora_A rows (c0 / 64 k-blocks)
+          for (int k0 = 0; k0 < p.lora_kb; ++k0) {
+            acquire();
+            if (lead) {
+              mbar_expect_tx(fb, static_cast<uint32_t>(kABytes));
+              tma_load_4d(d, &tmA0, fb, k0 * kBlockK, 0, h0, n0);
             }
-            if (++s == p.stages) { s = 0; ph ^= 1; }
           }
         }
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          // (a look-ahead test_wait on the next stage was measured: slower -- the producer usually runs ahead, the
-          //  poll fails and the blocking wait still follows)
-          if (fills >= p.stages) mbar_wait(&empty_bar[s], ph ^ 1);       // fresh barriers: the first pass never waits
-          uint8_t* dst = smem + s * stage_bytes;
-          uint64_t* fb = &full_bar[s];
-          int s_next = s + 1;
-          uint32_t ph_next = ph;
-          if (s_next == p.stages) { s_next = 0; ph_next ^= 1; }
-          ++fills;
-          if ((p.debug & 1) && ph) {                       // timing experiment: operands stay whatever is in smem
-            if (cta_rank == 0) mbar_arrive(fb);
+        // ---- segment 0: taps x channel blocks of the main input (three literal tensor-map operands: selecting the
+        //      map through a pointer variable is slower)
+        const int end0 = min(kb_end, seg_end0);
+        while (kb < end0) {
+          const int n = min(cb0 - cb, end0 - kb);
+          const int hh = h0 + dh;
+          int c = cb * kBlockK;
+          for (int i = 0; i < n; ++i, c += kBlockK) {
+            acquire();
+            if (lead) {
+              if (expect) mbar_expect_tx(fb, a_bytes);
+              if (kCta2) tma_load_4d_cta2(d, &tmA0, fb, c, dw, hh, n0);
+              else tma_load_4d(d, &tmA0, fb, c, dw, hh, n0);
+            }
+            PKB(64, kb + i - kb_begin);
+          }
+          kb += n;
+          cb = 0;
+          if (++dw == 2) { dw = -1; ++dh; }
+        }
+        // ---- segment 1: the second input of a concatenation (or, fused LoRA: the T tile, already in shared memory)
+        const int end1 = min(kb_end, seg_end1);
+        for (int c = (kb - seg_end0) * kBlockK; kb < end1; ++kb, c += kBlockK) {
+          acquire();
+          if (!lead) continue;
+          if (kLora) {
+            mbar_expect_tx(fb, 0u);
           } else {
-            const bool lora_block = kLora && seg == 1;     // its A operand is the T tile in shared memory
-            if (expect) mbar_expect_tx(fb, lora_block ? my_bytes - (do_a ? static_cast<uint32_t>(kABytes) : 0u) : my_bytes);
-            if (do_a && !lora_block) {
-              // (three literal tensor-map operands: selecting the map through a pointer variable is slower)
-              const int c0 = cb * kBlockK;
-              if (kCta2) {
-                if (seg == 0) tma_load_4d_cta2(dst, &tmA0, fb, c0, dw, h0 + dh, n0);
-                else if (seg == 1) tma_load_4d_cta2(dst, &tmA1, fb, c0, 0, h0, n0);
-                else tma_load_4d_cta2(dst, &tmA2, fb, c0, 0, h0, n0);
-              } else {
-                if (seg == 0) tma_load_4d(dst, &tmA0, fb, c0, dw, h0 + dh, n0);
-                else if (seg == 1) tma_load_4d(dst, &tmA1, fb, c0, 0, h0, n0);
-                else tma_load_4d(dst, &tmA2, fb, c0, 0, h0, n0);
-              }
-            }
-            if (do_b) {
-              if (kCta2) tma_load_2d_cta2(dst + kABytes, &tmB, fb, kb * kBlockK, b_row0);
-              else tma_load_2d(dst + kABytes, &tmB, fb, kb * kBlockK, b_row0);
-            }
+            if (expect) mbar_expect_tx(fb, a_bytes);
+            if (kCta2) tma_load_4d_cta2(d, &tmA1, fb, c, 0, h0, n0);
+            else tma_load_4d(d, &tmA1, fb, c, 0, h0, n0);
           }
-          // advance the k-block state
-          ++cb;
-          if (seg == 0) {
-            if (cb == p.cb0) {
-              cb = 0;
-              if (++tap == p.ntaps) { seg = 1; dh = 0; dw = 0; if (p.seg_end1 == p.seg_end0) seg = 2; }
-              else if (++dw == 2) { dw = -1; ++dh; }
-            }
-          } else if (seg == 1 && kb + 1 == p.seg_end1) {
-            seg = 2;
-            cb = 0;
+        }
+        // ---- segment 2: the third input
+        for (int c = (kb - seg_end1) * kBlockK; kb < kb_end; ++kb, c += kBlockK) {
+          acquire();
+          if (lead) {
+            if (expect) mbar_expect_tx(fb, a_bytes);
+            if (kCta2) tma_load_4d_cta2(d, &tmA2, fb, c, 0, h0, n0);
+            else tma_load_4d(d, &tmA2, fb, c, 0, h0, n0);
           }
-          s = s_next;
-          ph = ph_next;
         }
       }
-      if (do_a) TL(5);
+      TL(5);
+    }
+  } else if (warp == kProducerBWarp) {
+    // ================================================================ weight (B) TMA producer (same structure)
+    {
+      const bool lead = elect_one();
+      const int stages = p.stages;
+      const uint32_t stage_b = stage_bytes;
+      const uint32_t smem_b = smem_u32(smem) + kABytes, full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+      const uint32_t ring_end = smem_b + stages * stage_b;
+      const uint32_t b_bytes = static_cast<uint32_t>(stage_bytes - kABytes) * (kCta2 ? 2u : 1u);
+      const bool expect = !kCta2 || cta_rank == 0;
+      uint32_t slot = smem_b, bar_off = 0, ph = 0;
+      uint32_t d, fb;
+      auto acquire = [&]() {
+        mbar_wait(empty_a + bar_off, ph ^ 1);
+        d = slot;
+        fb = full_a + bar_off;
+        slot += stage_b;
+        bar_off += 8;
+        if (slot == ring_end) { slot = smem_b; bar_off = 0; ph ^= 1; }
+      };
+      for (int t = tile0; t < num_tiles; t += tile_step) {
+        const int tn = p.num_n_tiles == 1 ? t : t / p.num_n_tiles;
+        const int n_tile = t - tn * p.num_n_tiles;
+        const int split = p.ksplit == 1 ? 0 : tn / p.num_m_groups;
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+        const int b_row0 = n_tile * p.block_n + static_cast<int>(cta_rank) * b_rows;
+        if (kLora) {
+          const uint32_t bytes0 = static_cast<uint32_t>(p.lora_n) * kBlockK * 2;
+          for (int k0 = 0; k0 < p.lora_kb; ++k0) {
+            acquire();
+            if (lead) {
+              mbar_expect_tx(fb, bytes0);
+              tma_load_2d(d, &tmLA, fb, k0 * kBlockK, 0);
+            }
+          }
+        }
+        int c = kb_begin * kBlockK;
+        for (int kb = kb_begin; kb < kb_end; ++kb, c += kBlockK) {
+          acquire();
+          if (lead) {
+            if (expect) mbar_expect_tx(fb, b_bytes);
+            if (kCta2) tma_load_2d_cta2(d, &tmB, fb, c, b_row0);
+            else tma_load_2d(d, &tmB, fb, c, b_row0);
+          }
+          PKB(96, kb - kb_begin);
+        }
+      }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (one thread, leader CTA only)
-    if (lane == 0 && cta_rank == 0) {
+    // The WHOLE warp runs the loop and waits on the barriers; one elected lane issues.  With warp-uniform control
+    // flow the descriptors, TMEM and barrier addresses live in uniform registers, so a tcgen05.mma is one instruction
+    // instead of an ELECT + five R2UR.BROADCAST waterfall in front of each (measured 75 -> ~?? cycles per MMA).
+    if (cta_rank == 0) {
+      const bool lead = elect_one();
       const uint32_t idesc = make_idesc_bf16(kCta2 ? 2 * kBlockM : kBlockM, p.block_n, 0, 0);
       // K-major, 128B swizzle: 8-row atom = 1024 B -> SBO = 1024; LBO unused (1).  Stage s adds s * stage_bytes.
       const uint64_t a_desc0 = make_smem_desc(smem_u32(smem), 16, 1024, SWZ_128B);
       const uint64_t b_desc0 = make_smem_desc(smem_u32(smem) + kABytes, 16, 1024, SWZ_128B);
       const uint64_t desc_step = static_cast<uint64_t>(stage_bytes >> 4);
       uint64_t a_desc = a_desc0, b_desc = b_desc0;
-      int s = 0;
-      uint32_t ph = 0;
+      // (like the producers: ring state in registers, 32-bit barrier addresses, nothing re-read per k-block)
+      const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+      const uint32_t bar_end = static_cast<uint32_t>(p.stages) * 8u;
+      uint32_t bar_off = 0, ph = 0;
+      auto advance = [&]() {
+        a_desc += desc_step;
+        b_desc += desc_step;
+        bar_off += 8;
+        if (bar_off == bar_end) { bar_off = 0; ph ^= 1; a_desc = a_desc0; b_desc = b_desc0; }
+      };
       int it = 0;
       for (int t = tile0; t < num_tiles; t += tile_step, ++it) {
         const int buf = it & 1;
@@ -337,87 +401,82 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const uint32_t idesc_t = make_idesc_bf16(kBlockM, p.lora_n, 0, 0);
           const uint32_t t_tmem = tmem_base + 2 * p.block_n;
           for (int kb = 0; kb < p.lora_kb; ++kb) {
-            mbar_wait(&full_bar[s], ph);
+            mbar_wait(full_a + bar_off, ph);
             tc_fence_after();
-            umma_bf16_ss(t_tmem, a_desc, b_desc, idesc_t, kb != 0);
-            umma_bf16_ss(t_tmem, a_desc + 2, b_desc + 2, idesc_t, 1);
-            umma_bf16_ss(t_tmem, a_desc + 4, b_desc + 4, idesc_t, 1);
-            umma_bf16_ss(t_tmem, a_desc + 6, b_desc + 6, idesc_t, 1);
-            umma_commit(&empty_bar[s]);
-            a_desc += desc_step;
-            b_desc += desc_step;
-            if (++s == p.stages) { s = 0; ph ^= 1; a_desc = a_desc0; b_desc = b_desc0; }
+            if (lead) {
+              umma_bf16_ss(t_tmem, a_desc, b_desc, idesc_t, kb != 0);
+              umma_bf16_ss(t_tmem, a_desc + 2, b_desc + 2, idesc_t, 1);
+              umma_bf16_ss(t_tmem, a_desc + 4, b_desc + 4, idesc_t, 1);
+              umma_bf16_ss(t_tmem, a_desc + 6, b_desc + 6, idesc_t, 1);
+              umma_commit(empty_a + bar_off);
+            }
+            advance();
           }
-          umma_commit(lt_tmem_bar);
+          if (lead) umma_commit(lt_tmem_bar);
         }
         mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * p.block_n;
-        const int split = t / (p.num_n_tiles * p.num_m_groups);
+        const int split = p.ksplit == 1 ? 0 : t / (p.num_n_tiles * p.num_m_groups);
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+        const int kb_lora = kLora ? p.seg_end0 : -1;
         if (it == 0) TL(6);
-        long long acc_wait = 0, acc_test = 0, acc_fence = 0, acc_mma = 0, acc_rest = 0, n_blocked = 0, tq = 0;
+        [[maybe_unused]] long long acc_wait = 0, acc_mma = 0, tq = 0;
 #if B200_GEMM_PROFILE
-        const bool prof = (p.debug & 8) && blockIdx.x == 0;
+        const bool prof = (p.debug & 8) && blockIdx.x == 0 && lead;
+        const bool no_mma = p.debug & 2;
 #else
-        constexpr bool prof = false;
+        constexpr bool prof = false, no_mma = false;
 #endif
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           if (prof) tq = clock64();
-          mbar_wait(&full_bar[s], ph);
-          if (prof) { const long long now = clock64(); acc_wait += now - tq; tq = now; }
-          int s_next = s + 1;
-          uint32_t ph_next = ph;
-          if (s_next == p.stages) { s_next = 0; ph_next ^= 1; }
-          if (prof) { const long long now = clock64(); acc_test += now - tq; tq = now; }
+          mbar_wait(full_a + bar_off, ph);
           tc_fence_after();
-          if (prof) { const long long now = clock64(); acc_fence += now - tq; tq = now; }
-          if (kLora && kb == p.seg_end0) {
+          if (prof) { const long long now = clock64(); acc_wait += now - tq; tq = now; }
+          PKB(32, kb - kb_begin);
+          const uint32_t acc0 = kb != kb_begin;
+          if (kLora && kb == kb_lora) {
             // the LoRA k-block: A = T (written by the epilogue warps during the base k-blocks), B = s.B from the ring
             mbar_wait(lt_smem_bar, it & 1);
             tc_fence_after();
             const uint64_t t_desc = make_smem_desc(smem_u32(t_tile), 16, 1024, SWZ_128B);
-            const uint32_t acc0 = kb != kb_begin;
-            umma_bf16_ss(d_tmem, t_desc, b_desc, idesc, acc0);
-            umma_bf16_ss(d_tmem, t_desc + 2, b_desc + 2, idesc, 1);
-            umma_bf16_ss(d_tmem, t_desc + 4, b_desc + 4, idesc, 1);
-            umma_bf16_ss(d_tmem, t_desc + 6, b_desc + 6, idesc, 1);
-            umma_commit(&empty_bar[s]);
-          } else if (!(p.debug & 2)) {
-            const uint32_t acc0 = kb != kb_begin;
+            if (lead) {
+              umma_bf16_ss(d_tmem, t_desc, b_desc, idesc, acc0);
+              umma_bf16_ss(d_tmem, t_desc + 2, b_desc + 2, idesc, 1);
+              umma_bf16_ss(d_tmem, t_desc + 4, b_desc + 4, idesc, 1);
+              umma_bf16_ss(d_tmem, t_desc + 6, b_desc + 6, idesc, 1);
+              umma_commit(empty_a + bar_off);
+            }
+          } else if (kCta2) {
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
-            if (kCta2) {
+            if (lead) {
               umma_bf16_ss_cta2(d_tmem, a_desc, b_desc, idesc, acc0);
               umma_bf16_ss_cta2(d_tmem, a_desc + 2, b_desc + 2, idesc, 1);
               umma_bf16_ss_cta2(d_tmem, a_desc + 4, b_desc + 4, idesc, 1);
               umma_bf16_ss_cta2(d_tmem, a_desc + 6, b_desc + 6, idesc, 1);
-              umma_commit_cta2(&empty_bar[s], 3);          // frees the stage in both CTAs
-            } else {
+              umma_commit_cta2(empty_a + bar_off, 3);          // frees the stage in both CTAs
+            }
+          } else if (lead) {
+            if (!no_mma) {
               umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, acc0);
               umma_bf16_ss(d_tmem, a_desc + 2, b_desc + 2, idesc, 1);
               umma_bf16_ss(d_tmem, a_desc + 4, b_desc + 4, idesc, 1);
               umma_bf16_ss(d_tmem, a_desc + 6, b_desc + 6, idesc, 1);
-              umma_commit(&empty_bar[s]);
             }
-          } else {
-            if (kCta2) umma_commit_cta2(&empty_bar[s], 3);
-            else umma_commit(&empty_bar[s]);
+            umma_commit(empty_a + bar_off);
           }
+          advance();
           if (prof) { const long long now = clock64(); acc_mma += now - tq; tq = now; }
-          a_desc += desc_step;
-          b_desc += desc_step;
-          if (s_next == 0) { a_desc = a_desc0; b_desc = b_desc0; }
-          s = s_next;
-          ph = ph_next;
-          if (prof) { const long long now = clock64(); acc_rest += now - tq; tq = now; }
+          PKB(128, kb - kb_begin);
         }
-        if (prof && it == 0) {
-          g_timeline[25] = acc_wait; g_timeline[26] = acc_test; g_timeline[27] = acc_fence; g_timeline[28] = acc_mma;
-          g_timeline[29] = acc_rest; g_timeline[30] = n_blocked; g_timeline[31] = kb_end - kb_begin;
+        if (prof && lead && it == 0) {
+          g_timeline[25] = acc_wait; g_timeline[28] = acc_mma; g_timeline[31] = kb_end - kb_begin;
         }
-        if (kCta2) umma_commit_cta2(&tfull_bar[buf], 3);     // both CTAs' epilogues own 128 rows each
-        else umma_commit(&tfull_bar[buf]);
+        if (lead) {
+          if (kCta2) umma_commit_cta2(&tfull_bar[buf], 3);     // both CTAs' epilogues own 128 rows each
+          else umma_commit(&tfull_bar[buf]);
+        }
         if (it == 0) TL(10);
       }
     }
@@ -733,7 +792,7 @@ using namespace b200;
 
 // Debug only (not part of the product API surface beyond the header note): copy the CTA-0 timeline out.
 extern "C" int b200_debug_timeline(unsigned long long* host_out, int n) {
-  if (n > 32) n = 32;
+  if (n > 160) n = 160;
   cudaError_t e = cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * n);
   return e == cudaSuccess ? B200_OK : fail(B200_ERR_CUDA, "debug_timeline: %s", cudaGetErrorString(e));
 }

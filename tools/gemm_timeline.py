@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """CTA-0 cycle timeline of one b200_conv_gemm launch (run with B200_GEMM_DEBUG=4)."""
 import ctypes
+import os
 import sys
 from pathlib import Path
 
@@ -15,7 +16,10 @@ NAMES = {0: "entry", 1: "prologue done", 2: "pdl_wait done", 3: "producer: 1st T
          20: "epi c2: math done", 21: "epi c2: staging free", 22: "epi c2: smem written", 23: "epi c2: store issued",
          12: "epi: tfull seen", 13: "epi: tile done", 14: "epi: stores complete", 15: "exit"}
 g = torch.Generator().manual_seed(0)
-cases = [("conv L1 256->256", 16, 125, 8, 256, 256, 9), ("lin L3 640->640", 1, 1024, 1, 640, 640, 1)]
+cases = [("conv L0 128->128", 16, 250, 16, 128, 128, 9), ("conv L1 256->256", 16, 125, 8, 256, 256, 9),
+         ("lin L3 640->640", 1, 1024, 1, 640, 640, 1)]
+if len(sys.argv) > 1:
+    cases = cases[:int(sys.argv[1])]
 for label, nb, hh, ww, ci, co, taps in cases:
     x = torch.randn(nb * hh * ww, ci, generator=g).to("cuda", torch.bfloat16)
     wt = torch.randn(co, taps * ci, generator=g) * (taps * ci) ** -0.5
@@ -23,10 +27,10 @@ for label, nb, hh, ww, ci, co, taps in cases:
     bn = ops.choose_block_n(co, ops.num_m_tiles(nb, hh, ww))
     pw = packing.pack([wt], torch.zeros(co), bn, taps, ci, device="cuda")
     for _ in range(3):
-        ops.conv_gemm(pw, x, nb, hh, ww, out)
+        ops.conv_gemm(pw, x, nb, hh, ww, out, max_ctas=int(os.environ.get('MAXCTAS', '0')))
     torch.cuda.synchronize()
-    buf = (ctypes.c_ulonglong * 32)()
-    _lib.check(_lib.load().b200_debug_timeline(ctypes.cast(buf, ctypes.c_void_p), 32), "timeline")
+    buf = (ctypes.c_ulonglong * 160)()
+    _lib.check(_lib.load().b200_debug_timeline(ctypes.cast(buf, ctypes.c_void_p), 160), "timeline")
     t0 = buf[0]
     print(f"== {label} bn={bn}")
     for i in sorted(NAMES):
@@ -34,5 +38,10 @@ for label, nb, hh, ww, ci, co, taps in cases:
             print(f"   {NAMES[i]:<28} +{buf[i] - t0:>7} cyc")
     if buf[31]:
         n = buf[31]
-        print(f"   MMA thread over {n} k-blocks: wait {buf[25] / n:.0f}  test_wait {buf[26] / n:.0f}  fence {buf[27] / n:.0f}  "
-              f"mma+commit {buf[28] / n:.0f}  rest {buf[29] / n:.0f} cyc/kb; blocked waits {buf[30]}")
+        print(f"   MMA thread over {n} k-blocks of the first tile: wait for operands {buf[25] / n:.0f}  issue+commit+advance {buf[28] / n:.0f} cyc/kb")
+    if buf[32]:
+        n = buf[31]
+        base = buf[2]
+        print("   kb: A issued / B issued / operands seen by MMA thread / MMAs issued+committed   (cycles after pdl_wait)")
+        for k in range(min(n, 32)):
+            print(f"   {k:>3}: {int(buf[64 + k]) - int(base):>7} {int(buf[96 + k]) - int(base):>7} {int(buf[32 + k]) - int(base):>7} {int(buf[128 + k]) - int(base):>7}")
