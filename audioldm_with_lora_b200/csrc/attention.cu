@@ -208,17 +208,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 
   if (warp == 4) {
     // ============================================================ TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(q_full, kTileBytes);
-      tma_load_4d(sQ, &tmQKV, q_full, 0, q0, chunk_q, b);
+    // (the whole warp runs the loop with uniform control flow and one lane, elected at each use, issues: operands
+    //  stay in uniform registers instead of an ELECT + R2UR.BROADCAST waterfall in front of every TMA / MMA)
+    {
+      if (elect_one()) {
+        mbar_expect_tx(q_full, kTileBytes);
+        tma_load_4d(sQ, &tmQKV, q_full, 0, q0, chunk_q, b);
+      }
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < p.nblk; ++j) {
         mbar_wait(&kv_empty[s], ph ^ 1);
         uint8_t* k_dst = sKV + s * kStageBytes;
-        mbar_expect_tx(&kv_full[s], 2 * kKVTile);
-        tma_load_4d(k_dst, &tmKV, &kv_full[s], 0, j * kKV, chunk_k, b);
-        tma_load_4d(k_dst + kKVTile, &tmKV, &kv_full[s], 0, j * kKV, chunk_v, b);
+        if (elect_one()) {
+          mbar_expect_tx(&kv_full[s], 2 * kKVTile);
+          tma_load_4d(k_dst, &tmKV, &kv_full[s], 0, j * kKV, chunk_k, b);
+          tma_load_4d(k_dst + kKVTile, &tmKV, &kv_full[s], 0, j * kKV, chunk_v, b);
+        }
         if (++s == p.stages) {
           s = 0;
           ph ^= 1;
@@ -226,8 +232,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       }
     }
   } else if (warp == 5) {
-    // ============================================================ MMA issuer
-    if (lane == 0) {
+    // ============================================================ MMA issuer (whole warp, elected lane issues)
+    {
       const uint32_t idesc_s = make_idesc_bf16(128, KV, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(128, kOCols, 0, 1);  // B = [V | 1], MN-major
       // no-swizzle canonical layouts: core matrix = 8 rows x 16 B, contiguous (128 B).
@@ -247,24 +253,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         mbar_wait(&kv_full[s], ph);
         tc_fence_after();
         // S = Q K^T   (the previous block's softmax finished reading S before it released p_full)
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint64_t a_desc = make_smem_desc(q_addr + k * 4096, q_lbo, q_sbo, SWZ_NONE);
-          const uint64_t b_desc = make_smem_desc(k_addr + k * 2 * kChunk, k_lbo, k_sbo, SWZ_NONE);
-          umma_bf16_ss(t_s, a_desc, b_desc, idesc_s, k != 0);
+          for (int k = 0; k < D / 16; ++k) {
+            const uint64_t a_desc = make_smem_desc(q_addr + k * 4096, q_lbo, q_sbo, SWZ_NONE);
+            const uint64_t b_desc = make_smem_desc(k_addr + k * 2 * kChunk, k_lbo, k_sbo, SWZ_NONE);
+            umma_bf16_ss(t_s, a_desc, b_desc, idesc_s, k != 0);
+          }
+          umma_commit(s_full);
         }
-        umma_commit(s_full);
         // O += P [V | 1]   (the softmax threads rescaled O, if needed, before they released p_full)
         mbar_wait(p_full, j & 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kKV / 16; ++k) {
-          const uint64_t a_desc = make_smem_desc(p_addr + k * 4096, q_lbo, q_sbo, SWZ_NONE);
-          const uint64_t b_desc = make_smem_desc(v_addr + k * 256, v_lbo, v_sbo, SWZ_NONE);
-          umma_bf16_ss(t_o, a_desc, b_desc, idesc_o, (j | k) != 0);
+          for (int k = 0; k < kKV / 16; ++k) {
+            const uint64_t a_desc = make_smem_desc(p_addr + k * 4096, q_lbo, q_sbo, SWZ_NONE);
+            const uint64_t b_desc = make_smem_desc(v_addr + k * 256, v_lbo, v_sbo, SWZ_NONE);
+            umma_bf16_ss(t_o, a_desc, b_desc, idesc_o, (j | k) != 0);
+          }
+          umma_commit(o_full);
+          umma_commit(&kv_empty[s]);
         }
-        umma_commit(o_full);
-        umma_commit(&kv_empty[s]);
         if (++s == p.stages) {
           s = 0;
           ph ^= 1;

@@ -120,27 +120,32 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 
   if (warp == 4) {
     // ============================================================ TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(x_full, 2 * kTileBytes);
-      if (kModeQ) {
-        tma_load_4d(sX1, &tmQKV, x_full, 0, r0, chunk_q, b);
-        tma_load_4d(sX2, &tmDO, x_full, 0, r0, chunk_q, b);
-      } else {
-        tma_load_4d(sX1, &tmQKV, x_full, 0, r0, chunk_k, b);
-        tma_load_4d(sX2, &tmQKV, x_full, 0, r0, chunk_v, b);
+    // (whole warp, uniform control flow, one lane elected at each use issues -- see conv_gemm.cu)
+    {
+      if (elect_one()) {
+        mbar_expect_tx(x_full, 2 * kTileBytes);
+        if (kModeQ) {
+          tma_load_4d(sX1, &tmQKV, x_full, 0, r0, chunk_q, b);
+          tma_load_4d(sX2, &tmDO, x_full, 0, r0, chunk_q, b);
+        } else {
+          tma_load_4d(sX1, &tmQKV, x_full, 0, r0, chunk_k, b);
+          tma_load_4d(sX2, &tmQKV, x_full, 0, r0, chunk_v, b);
+        }
       }
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < p.nblk; ++j) {
         mbar_wait(&y_empty[s], ph ^ 1);
         uint8_t* dst = sY + s * 2 * kYTile;
-        mbar_expect_tx(&y_full[s], 2 * kYTile);
-        if (kModeQ) {
-          tma_load_4d(dst, &tmQKVc, &y_full[s], 0, j * BC, chunk_k, b);
-          tma_load_4d(dst + kYTile, &tmQKVc, &y_full[s], 0, j * BC, chunk_v, b);
-        } else {
-          tma_load_4d(dst, &tmQKVc, &y_full[s], 0, j * BC, chunk_q, b);
-          tma_load_4d(dst + kYTile, &tmDOc, &y_full[s], 0, j * BC, chunk_q, b);
+        if (elect_one()) {
+          mbar_expect_tx(&y_full[s], 2 * kYTile);
+          if (kModeQ) {
+            tma_load_4d(dst, &tmQKVc, &y_full[s], 0, j * BC, chunk_k, b);
+            tma_load_4d(dst + kYTile, &tmQKVc, &y_full[s], 0, j * BC, chunk_v, b);
+          } else {
+            tma_load_4d(dst, &tmQKVc, &y_full[s], 0, j * BC, chunk_q, b);
+            tma_load_4d(dst + kYTile, &tmDOc, &y_full[s], 0, j * BC, chunk_q, b);
+          }
         }
         if (++s == p.stages) {
           s = 0;
@@ -149,8 +154,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       }
     }
   } else if (warp == 5) {
-    // ============================================================ MMA issuer
-    if (lane == 0) {
+    // ============================================================ MMA issuer (whole warp, elected lane issues)
+    {
       const uint32_t idesc_t = make_idesc_bf16(128, BC, 0, 0);        // T = X Y^T, both K-major
       const uint32_t idesc_a = make_idesc_bf16(128, D, 0, 1);         // Acc += P Y, Y MN-major
       const uint32_t x1_addr = smem_u32(sX1), x2_addr = smem_u32(sX2);
@@ -163,38 +168,42 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const uint32_t y2_addr = y1_addr + kYTile;
         mbar_wait(&y_full[s], ph);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint64_t a_desc = make_smem_desc(x1_addr + k * 4096, 2048, 128, SWZ_NONE);
-          const uint64_t b_desc = make_smem_desc(y1_addr + k * 2 * kChunkY, kChunkY, 128, SWZ_NONE);
-          umma_bf16_ss(t_1, a_desc, b_desc, idesc_t, k != 0);
-        }
+          for (int k = 0; k < D / 16; ++k) {
+            const uint64_t a_desc = make_smem_desc(x1_addr + k * 4096, 2048, 128, SWZ_NONE);
+            const uint64_t b_desc = make_smem_desc(y1_addr + k * 2 * kChunkY, kChunkY, 128, SWZ_NONE);
+            umma_bf16_ss(t_1, a_desc, b_desc, idesc_t, k != 0);
+          }
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint64_t a_desc = make_smem_desc(x2_addr + k * 4096, 2048, 128, SWZ_NONE);
-          const uint64_t b_desc = make_smem_desc(y2_addr + k * 2 * kChunkY, kChunkY, 128, SWZ_NONE);
-          umma_bf16_ss(t_2, a_desc, b_desc, idesc_t, k != 0);
+          for (int k = 0; k < D / 16; ++k) {
+            const uint64_t a_desc = make_smem_desc(x2_addr + k * 4096, 2048, 128, SWZ_NONE);
+            const uint64_t b_desc = make_smem_desc(y2_addr + k * 2 * kChunkY, kChunkY, 128, SWZ_NONE);
+            umma_bf16_ss(t_2, a_desc, b_desc, idesc_t, k != 0);
+          }
+          umma_commit(t_full);
         }
-        umma_commit(t_full);
         // the elementwise threads have turned T1 / T2 into P^T / dS^T in shared memory
         mbar_wait(ps_full, j & 1);
         tc_fence_after();
-        if (!kModeQ) {
+        if (elect_one()) {
+          if (!kModeQ) {
+#pragma unroll
+            for (int k = 0; k < BC / 16; ++k) {
+              const uint64_t a_desc = make_smem_desc(p_addr + k * 4096, 2048, 128, SWZ_NONE);
+              const uint64_t b_desc = make_smem_desc(y2_addr + k * 256, 128, kChunkY, SWZ_NONE);
+              umma_bf16_ss(t_a1, a_desc, b_desc, idesc_a, (j | k) != 0);
+            }
+          }
 #pragma unroll
           for (int k = 0; k < BC / 16; ++k) {
-            const uint64_t a_desc = make_smem_desc(p_addr + k * 4096, 2048, 128, SWZ_NONE);
-            const uint64_t b_desc = make_smem_desc(y2_addr + k * 256, 128, kChunkY, SWZ_NONE);
-            umma_bf16_ss(t_a1, a_desc, b_desc, idesc_a, (j | k) != 0);
+            const uint64_t a_desc = make_smem_desc(ds_addr + k * 4096, 2048, 128, SWZ_NONE);
+            const uint64_t b_desc = make_smem_desc(y1_addr + k * 256, 128, kChunkY, SWZ_NONE);
+            umma_bf16_ss(t_a2, a_desc, b_desc, idesc_a, (j | k) != 0);
           }
+          umma_commit(&y_empty[s]);
+          if (j == p.nblk - 1) umma_commit(acc_full);
         }
-#pragma unroll
-        for (int k = 0; k < BC / 16; ++k) {
-          const uint64_t a_desc = make_smem_desc(ds_addr + k * 4096, 2048, 128, SWZ_NONE);
-          const uint64_t b_desc = make_smem_desc(y1_addr + k * 256, 128, kChunkY, SWZ_NONE);
-          umma_bf16_ss(t_a2, a_desc, b_desc, idesc_a, (j | k) != 0);
-        }
-        umma_commit(&y_empty[s]);
-        if (j == p.nblk - 1) umma_commit(acc_full);
         if (++s == p.stages) {
           s = 0;
           ph ^= 1;

@@ -224,8 +224,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // warp-uniform control flow (coordinates and addresses in uniform registers, one elected lane issues: no
     // ELECT + R2UR.BROADCAST waterfall per TMA), 32-bit shared-window addresses advanced incrementally, the (segment,
     // tap, channel-block) walk as nested loops instead of a per-k-block state machine, the watchdog out of line.
+    // (The lane is elected at every use: a loop-invariant predicate gets the loop unswitched into a one-lane copy,
+    //  i.e. divergent code, and the waterfalls come back.)
     {
-      const bool lead = elect_one();
       const int stages = p.stages, cb0 = p.cb0;
       const int seg_end0 = p.seg_end0, seg_end1 = p.seg_end1;
       const uint32_t stage_b = stage_bytes;
@@ -269,7 +270,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           // ---- phase 0: the tile's activations once more, against the stacked lora_A rows (c0 / 64 k-blocks)
           for (int k0 = 0; k0 < p.lora_kb; ++k0) {
             acquire();
-            if (lead) {
+            if (elect_one()) {
               mbar_expect_tx(fb, static_cast<uint32_t>(kABytes));
               tma_load_4d(d, &tmA0, fb, k0 * kBlockK, 0, h0, n0);
             }
@@ -278,28 +279,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // ---- segment 0: taps x channel blocks of the main input (three literal tensor-map operands: selecting the
         //      map through a pointer variable is slower)
         const int end0 = min(kb_end, seg_end0);
-        while (kb < end0) {
-          const int n = min(cb0 - cb, end0 - kb);
-          const int hh = h0 + dh;
-          int c = cb * kBlockK;
-          for (int i = 0; i < n; ++i, c += kBlockK) {
+        {
+          int left = cb0 - cb;              // k-blocks left in the current tap
+          int c = cb * kBlockK, hh = h0 + dh;
+#pragma unroll 1
+          for (; kb < end0; ++kb) {
             acquire();
-            if (lead) {
+            if (elect_one()) {
               if (expect) mbar_expect_tx(fb, a_bytes);
               if (kCta2) tma_load_4d_cta2(d, &tmA0, fb, c, dw, hh, n0);
               else tma_load_4d(d, &tmA0, fb, c, dw, hh, n0);
             }
-            PKB(64, kb + i - kb_begin);
+            PKB(64, kb - kb_begin);
+            c += kBlockK;
+            if (--left == 0) {              // next tap: (dh, dw) walk the 3x3 window row by row
+              left = cb0;
+              c = 0;
+              if (++dw == 2) { dw = -1; ++hh; }
+            }
           }
-          kb += n;
-          cb = 0;
-          if (++dw == 2) { dw = -1; ++dh; }
         }
         // ---- segment 1: the second input of a concatenation (or, fused LoRA: the T tile, already in shared memory)
         const int end1 = min(kb_end, seg_end1);
+#pragma unroll 1
         for (int c = (kb - seg_end0) * kBlockK; kb < end1; ++kb, c += kBlockK) {
           acquire();
-          if (!lead) continue;
+          if (!elect_one()) continue;
           if (kLora) {
             mbar_expect_tx(fb, 0u);
           } else {
@@ -309,9 +314,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
         }
         // ---- segment 2: the third input
+#pragma unroll 1
         for (int c = (kb - seg_end1) * kBlockK; kb < kb_end; ++kb, c += kBlockK) {
           acquire();
-          if (lead) {
+          if (elect_one()) {
             if (expect) mbar_expect_tx(fb, a_bytes);
             if (kCta2) tma_load_4d_cta2(d, &tmA2, fb, c, 0, h0, n0);
             else tma_load_4d(d, &tmA2, fb, c, 0, h0, n0);
@@ -323,7 +329,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   } else if (warp == kProducerBWarp) {
     // ================================================================ weight (B) TMA producer (same structure)
     {
-      const bool lead = elect_one();
       const int stages = p.stages;
       const uint32_t stage_b = stage_bytes;
       const uint32_t smem_b = smem_u32(smem) + kABytes, full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
@@ -351,16 +356,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const uint32_t bytes0 = static_cast<uint32_t>(p.lora_n) * kBlockK * 2;
           for (int k0 = 0; k0 < p.lora_kb; ++k0) {
             acquire();
-            if (lead) {
+            if (elect_one()) {
               mbar_expect_tx(fb, bytes0);
               tma_load_2d(d, &tmLA, fb, k0 * kBlockK, 0);
             }
           }
         }
         int c = kb_begin * kBlockK;
+#pragma unroll 1
         for (int kb = kb_begin; kb < kb_end; ++kb, c += kBlockK) {
           acquire();
-          if (lead) {
+          if (elect_one()) {
             if (expect) mbar_expect_tx(fb, b_bytes);
             if (kCta2) tma_load_2d_cta2(d, &tmB, fb, c, b_row0);
             else tma_load_2d(d, &tmB, fb, c, b_row0);
@@ -429,6 +435,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #else
         constexpr bool prof = false, no_mma = false;
 #endif
+        // (a non-blocking look-ahead probe of the next slot's barrier before issuing was measured: slower -- the
+        //  loop is bound by the operand stream, the next slot is never ready at probe time)
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           if (prof) tq = clock64();
           mbar_wait(full_a + bar_off, ph);

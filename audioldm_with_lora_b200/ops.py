@@ -21,6 +21,7 @@ NUM_SMS = 148
 # 2-CTA (cta_group::2) GEMM tiles.  Correct and tested, but on the AudioLDM-S shapes (one 128 x block_n tile per CTA,
 # K <= 11.5k) the longer prologue / cluster syncs eat the mainloop gain (5.61 vs 5.57 ms per step): opt-in.
 CTA_PAIR = os.environ.get("B200_CTA_PAIR", "0") != "0"
+TMA_BYTES_PER_CLK = float(os.environ.get("B200_TMA_BPC", "55"))
 
 
 @dataclass
@@ -87,10 +88,11 @@ def choose_block_n(n: int, m_tiles: int, geglu: bool = False) -> int:
 
 
 def _kb_cycles(bn: int, pair: bool = False) -> float:
-    """Cycles one 64-deep K block costs a CTA: tcgen05 time (2*bn) or operand fetch (bytes / ~55 B/clk, the
-    latency-bound TMA rate measured with 4-8 stages in flight), whichever is larger.  In 2-CTA mode a CTA
+    """Cycles one 64-deep K block costs a CTA: tcgen05 time (2*bn) or operand fetch (bytes / TMA_BYTES_PER_CLK, the
+    per-SM TMA ingest rate measured with the CTA-0 timeline: independent of ring depth and of how many CTAs run),
+    whichever is larger.  In 2-CTA mode a CTA
     fetches its 128 A rows and only half of the weight tile."""
-    return max(2.0 * bn, (16384 + bn * (64 if pair else 128)) / 55.0)
+    return max(2.0 * bn, (16384 + bn * (64 if pair else 128)) / TMA_BYTES_PER_CLK)
 
 
 def choose_tiling(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_split: bool = True,

@@ -27,7 +27,7 @@ for label, nb, hh, ww, ci, co, taps in cases:
     bn = ops.choose_block_n(co, ops.num_m_tiles(nb, hh, ww))
     pw = packing.pack([wt], torch.zeros(co), bn, taps, ci, device="cuda")
     for _ in range(3):
-        ops.conv_gemm(pw, x, nb, hh, ww, out, max_ctas=int(os.environ.get('MAXCTAS', '0')))
+        ops.conv_gemm(pw, x, nb, hh, ww, out, max_ctas=int(os.environ.get('MAXCTAS', '0')), cta_pair=bool(int(os.environ.get('PAIR', '0'))))
     torch.cuda.synchronize()
     buf = (ctypes.c_ulonglong * 160)()
     _lib.check(_lib.load().b200_debug_timeline(ctypes.cast(buf, ctypes.c_void_p), 160), "timeline")
