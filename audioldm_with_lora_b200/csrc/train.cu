@@ -503,21 +503,24 @@ lora_wgrad_tc_kernel(const __grid_constant__ WgradTcMaps maps, const WgradParams
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();
+  // producer and MMA issuer: the whole warp runs the loop (uniform control flow), one lane elected at each use issues
   if (warp == 4) {
-    if (lane == 0) {
+    {
       int s = 0;
       uint32_t ph = 0;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* dst = smem + s * stage_bytes;
-        mbar_expect_tx(&full_bar[s], kABytes + b_bytes);
-        tma_load_4d(dst, &maps.u[blockIdx.z], &full_bar[s], 0, t * kWtTok, c0 / 8, 0);
-        tma_load_4d(dst + kABytes, &maps.v[blockIdx.z], &full_bar[s], 0, t * kWtTok, 0, 0);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[s], kABytes + b_bytes);
+          tma_load_4d(dst, &maps.u[blockIdx.z], &full_bar[s], 0, t * kWtTok, c0 / 8, 0);
+          tma_load_4d(dst + kABytes, &maps.v[blockIdx.z], &full_bar[s], 0, t * kWtTok, 0, 0);
+        }
         if (++s == kWtStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);      // A and B MN-major
       int s = 0;
       uint32_t ph = 0;
@@ -526,17 +529,19 @@ lora_wgrad_tc_kernel(const __grid_constant__ WgradTcMaps maps, const WgradParams
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
         const uint32_t b_addr = a_addr + kABytes;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kWtTok / 16; ++k) {
-          // MN-major: next 8-token K group +128 B (LBO), next 8-channel chunk + 64 tokens x 16 B = 1024 B (SBO)
-          const uint64_t a_desc = make_smem_desc(a_addr + k * 256, 128, kWtTok * 16, SWZ_NONE);
-          const uint64_t b_desc = make_smem_desc(b_addr + k * 256, 128, kWtTok * 16, SWZ_NONE);
-          umma_bf16_ss(tmem_base, a_desc, b_desc, idesc, (t != t_begin) || k != 0);
+          for (int k = 0; k < kWtTok / 16; ++k) {
+            // MN-major: next 8-token K group +128 B (LBO), next 8-channel chunk + 64 tokens x 16 B = 1024 B (SBO)
+            const uint64_t a_desc = make_smem_desc(a_addr + k * 256, 128, kWtTok * 16, SWZ_NONE);
+            const uint64_t b_desc = make_smem_desc(b_addr + k * 256, 128, kWtTok * 16, SWZ_NONE);
+            umma_bf16_ss(tmem_base, a_desc, b_desc, idesc, (t != t_begin) || k != 0);
+          }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
         if (++s == kWtStages) { s = 0; ph ^= 1; }
       }
-      umma_commit(acc_bar);
+      if (elect_one()) umma_commit(acc_bar);
     }
   } else {
     mbar_wait(acc_bar, 0);

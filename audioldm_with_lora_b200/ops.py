@@ -21,7 +21,7 @@ NUM_SMS = 148
 # 2-CTA (cta_group::2) GEMM tiles.  Correct and tested, but on the AudioLDM-S shapes (one 128 x block_n tile per CTA,
 # K <= 11.5k) the longer prologue / cluster syncs eat the mainloop gain (5.61 vs 5.57 ms per step): opt-in.
 CTA_PAIR = os.environ.get("B200_CTA_PAIR", "0") != "0"
-TMA_BYTES_PER_CLK = float(os.environ.get("B200_TMA_BPC", "55"))
+TMA_BYTES_PER_CLK = float(os.environ.get("B200_TMA_BPC", "80"))    # measured: profiles/r01_gemm_mainloop_timeline.md
 
 
 @dataclass
