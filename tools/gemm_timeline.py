@@ -1,5 +1,19 @@
 #!/usr/bin/env python
-"""CTA-0 cycle timeline of one b200_conv_gemm launch (run with B200_GEMM_DEBUG=4)."""
+"""CTA-0 cycle timeline of one b200_conv_gemm launch: fixed points of the kernel, the MMA issuer's wait / issue split and
+the time stamp of every k-block's TMA issues and MMA issue in the first tile (profiles/r01_gemm_mainloop_timeline.md).
+
+Needs a profile build of the library (the product build carries no instrumentation):
+
+    cd audioldm_with_lora_b200 && mkdir -p variants && for f in conv_gemm attention attention_bwd norm sampler train; do
+      nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr \
+           -DB200_GEMM_PROFILE=1 -c csrc/$f.cu -o variants/$f.o; done
+    nvcc -shared -o variants/libb200ldm_prof.so variants/*.o -lcudart -gencode arch=compute_100a,code=sm_100a
+
+    B200LDM_LIB=audioldm_with_lora_b200/variants/libb200ldm_prof.so B200_GEMM_DEBUG=12 python tools/gemm_timeline.py [ncases]
+
+B200_GEMM_DEBUG bits: 2 = issue no MMAs (garbage results, timing only), 4 = timeline, 8 = per-k-block stamps.
+MAXCTAS=n caps the grid (is a limit per SM or chip-wide?), PAIR=1 runs the 2-CTA mode, B200_GEMM_STAGES=n caps the ring.
+"""
 import ctypes
 import os
 import sys
