@@ -20,7 +20,8 @@ Tensor = torch.Tensor
 NUM_SMS = 148
 # 2-CTA (cta_group::2) GEMM tiles.  Correct and tested, but on the AudioLDM-S shapes (one 128 x block_n tile per CTA,
 # K <= 11.5k) the longer prologue / cluster syncs eat the mainloop gain (5.61 vs 5.57 ms per step): opt-in.
-CTA_PAIR = os.environ.get("B200_CTA_PAIR", "0") != "0"
+CTA_PAIR = os.environ.get("B200_CTA_PAIR", "1") != "0"      # 2-CTA (cta_group::2) tiles where a layer qualifies
+PAIR_MIN_BN = int(os.environ.get("B200_PAIR_MIN_BN", "128"))     # 2-CTA tiles only for tiles at least this wide
 TMA_BYTES_PER_CLK = float(os.environ.get("B200_TMA_BPC", "80"))    # measured: profiles/r01_gemm_mainloop_timeline.md
 
 
@@ -105,7 +106,7 @@ def choose_tiling(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_
         if ks > 1 and (not allow_split or geglu or num_kb < 16 * ks // 2):
             continue
         for bn in range(step, max_bn + 1, step):
-            pair = CTA_PAIR and bn % 128 == 0 and m_tiles >= 2 and num_kb >= 16
+            pair = CTA_PAIR and bn % 128 == 0 and bn >= PAIR_MIN_BN and m_tiles >= 2 and num_kb >= 16
             tiles1 = (2 * math.ceil(m_tiles / 2) if pair else m_tiles) * math.ceil(n / bn)
             if ks > 1 and tiles1 > num_sms // 2:
                 continue
@@ -148,7 +149,7 @@ def conv_gemm(pw: PackedWeight, a0: Tensor, nb: int, h: int, w: int, out: Tensor
     call("b200_conv_gemm", ptr(a0), pw.c0, ptr(a1) if pw.c1 else None, pw.c1, ptr(a2) if pw.c2 else None, pw.c2,
          nb, h, w, pw.ntaps, stride, ptr(pw.w), pw.n_pad, pw.n_valid, ptr(pw.bias), ptr(rowvec), rowvec_ld,
          ptr(residual), res_ld, ptr(out), ld, int(out_fp32), int(pw.geglu), pw.block_n, max_ctas, ksplit,
-         ptr(workspace) if ksplit > 1 else None, (int(CTA_PAIR) if cta_pair is None else (2 if cta_pair else 0)), stream(), info=info)
+         ptr(workspace) if ksplit > 1 else None, (int(CTA_PAIR and pw.block_n >= PAIR_MIN_BN) if cta_pair is None else (2 if cta_pair else 0)), stream(), info=info)
     return out
 
 
