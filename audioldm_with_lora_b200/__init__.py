@@ -5,7 +5,8 @@ Compute runs in hand-written sm_100a kernels (csrc/, C-ABI in include/b200ldm.h)
 device memory and streams only.  There is no CPU or PyTorch fallback for the hot path.
 """
 from .arch import AUDIOLDM_L, AUDIOLDM_S, CONFIGS, UNetConfig
-from .lora import (LoraConfig, convert_state_dict_to_diffusers, parse_lora_state_dict, to_peft_state_dict)
+from .lora import (LoraConfig, convert_state_dict_to_diffusers, load_lora_checkpoint, merge_lora_into_state_dict,
+                   parse_lora_state_dict, save_lora_checkpoint, to_peft_state_dict)
 from .model import (Attention, B200AttnProcessor, LoraLinear, UNet2DConditionModel, UNet2DConditionOutput,
                     get_peft_model, get_peft_model_state_dict)
 from .pipeline import AudioLDMPipeline, AudioPipelineOutput
@@ -13,7 +14,8 @@ from .scheduler import DDIMScheduler, PNDMScheduler
 
 __all__ = [
     "AUDIOLDM_L", "AUDIOLDM_S", "CONFIGS", "UNetConfig", "LoraConfig", "convert_state_dict_to_diffusers",
-    "parse_lora_state_dict", "to_peft_state_dict", "Attention", "B200AttnProcessor", "LoraLinear",
+    "parse_lora_state_dict", "to_peft_state_dict", "save_lora_checkpoint", "load_lora_checkpoint",
+    "merge_lora_into_state_dict", "Attention", "B200AttnProcessor", "LoraLinear",
     "UNet2DConditionModel", "UNet2DConditionOutput", "get_peft_model", "get_peft_model_state_dict",
     "AudioLDMPipeline", "AudioPipelineOutput", "DDIMScheduler", "PNDMScheduler",
 ]

@@ -12,11 +12,21 @@ Accepted key formats (all map to the same adapter):
   2. base_model.model.<path>.<t>.lora_A.weight / lora_B.weight                       (get_peft_model_state_dict)
   3. [unet.]<path>.<t>.lora.down.weight / lora.up.weight                             (diffusers format)
 LoRA stays unmerged at run time: y = base(x) + B(A(x)) * (alpha / r) * scale.
+
+Checkpoint writers and the opt-in pre-merge:
+  * `save_lora_checkpoint(adapters, dir, fmt)` writes what the reference's tooling writes -- accelerate's
+    `save_state` file `model.safetensors` with full peft keys (train_audioldm_lora.py:575, read back by
+    generate_audio.py:32), the `get_peft_model_state_dict` layout, or diffusers' `pytorch_lora_weights.safetensors`
+    (`lora.down/up` keys, train_audioldm_lora.py:577-579 / app.py:11);
+  * `merge_lora_into_state_dict(sd, adapters, scale)` returns base weights with W' = W + (alpha / r) * scale * B A
+    folded in (peft `merge_and_unload`).  Never applied implicitly: the merged path rounds W' to bf16 once, the
+    unmerged path rounds W and the rank-r term separately, so the two are not bit-identical.
 """
 from __future__ import annotations
 
 import re
 from dataclasses import dataclass, field
+from pathlib import Path
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import torch
@@ -126,4 +136,74 @@ def convert_state_dict_to_diffusers(sd: Dict[str, Tensor]) -> Dict[str, Tensor]:
             continue
         is_a = (m.group("peft") == "lora_A") or (m.group("dfs") == "down")
         out[f"{m.group('path')}.lora.{'down' if is_a else 'up'}.weight"] = v
+    return out
+
+
+# ----------------------------------------------------------------------------- checkpoint writers, opt-in merge
+_CKPT_FILES = {"peft_full": "model.safetensors", "peft": "adapter_model.safetensors",
+               "diffusers": "pytorch_lora_weights.safetensors"}
+
+
+def lora_state_dict_as(adapters: Dict[str, LoraEntry], fmt: str = "peft", adapter_name: str = "default") -> Dict[str, Tensor]:
+    """The adapters under the keys of one of the three formats `parse_lora_state_dict` reads:
+    "peft_full" (accelerate save_state: `...lora_A.<adapter>.weight`), "peft" (`get_peft_model_state_dict`),
+    "diffusers" (`<path>.lora.down/up.weight`)."""
+    if fmt == "peft_full":
+        return to_peft_state_dict(adapters, adapter_name)
+    if fmt == "peft":
+        return to_peft_state_dict(adapters, None)
+    if fmt == "diffusers":
+        return convert_state_dict_to_diffusers(to_peft_state_dict(adapters, None))
+    raise ValueError(f"unknown LoRA checkpoint format {fmt!r} (peft_full | peft | diffusers)")
+
+
+def save_lora_checkpoint(adapters: Dict[str, LoraEntry], save_directory, fmt: str = "diffusers",
+                         adapter_name: str = "default", dtype: torch.dtype = torch.float32) -> Path:
+    """Write the adapters as a safetensors file named as the reference's tools name it (see the module docstring);
+    alpha / rank go into the file metadata (peft keeps them in adapter_config.json, diffusers in network_alphas).
+    Returns the file path; `UNet2DConditionModel.load_attn_procs(save_directory)` reads it back."""
+    from safetensors.torch import save_file
+    sd = {k: v.detach().to(dtype).contiguous().cpu() for k, v in lora_state_dict_as(adapters, fmt, adapter_name).items()}
+    out = Path(save_directory)
+    out.mkdir(parents=True, exist_ok=True)
+    ranks = sorted({int(e.A.shape[0]) for e in adapters.values()})
+    alphas = sorted({float(e.alpha) for e in adapters.values()})
+    meta = {"format": fmt, "r": ",".join(map(str, ranks)), "lora_alpha": ",".join(map(str, alphas))}
+    path = out / _CKPT_FILES[fmt]
+    save_file(sd, str(path), metadata=meta)
+    return path
+
+
+def load_lora_checkpoint(path, alpha: Optional[float] = None) -> Dict[str, LoraEntry]:
+    """Read any of the files `save_lora_checkpoint` (or the reference's tooling) writes.  alpha: explicit value, else
+    the file metadata when it names a single value, else rank (scaling 1, what the reference trains with)."""
+    from safetensors import safe_open
+    p = Path(path)
+    if p.is_dir():
+        cands = [p / f for f in ("pytorch_lora_weights.safetensors", "model.safetensors", "adapter_model.safetensors")]
+        p = next((c for c in cands if c.exists()), cands[0])
+    sd = {}
+    with safe_open(str(p), framework="pt") as f:
+        meta = f.metadata() or {}
+        for k in f.keys():
+            sd[k] = f.get_tensor(k)
+    if alpha is None and meta.get("lora_alpha") and "," not in meta["lora_alpha"]:
+        alpha = float(meta["lora_alpha"])
+    return parse_lora_state_dict(sd, alpha)
+
+
+def merge_lora_into_state_dict(sd: Dict[str, Tensor], adapters: Dict[str, LoraEntry], scale: float = 1.0,
+                               sign: float = 1.0) -> Dict[str, Tensor]:
+    """Copy of the base state dict with W' = W + sign * (alpha / r) * scale * B @ A for every adapted projection
+    (peft `merge_and_unload`; sign = -1 un-merges).  fp32 arithmetic; keys without an adapter are shared, not copied."""
+    out = dict(sd)
+    for path, e in adapters.items():
+        key = path + ".weight"
+        if key not in sd:
+            raise KeyError(f"adapter {path} has no base weight {key} in the state dict")
+        w = sd[key].detach().float()
+        if w.shape != (e.B.shape[0], e.A.shape[1]):
+            raise ValueError(f"{key}: base {tuple(w.shape)} vs B A {(e.B.shape[0], e.A.shape[1])}")
+        s_eff = sign * scale * e.alpha / e.A.shape[0]
+        out[key] = (w + s_eff * (e.B.float() @ e.A.float())).to(sd[key].dtype)
     return out

@@ -298,7 +298,7 @@ class UNet2DConditionModel(nn.Module):
             from safetensors.torch import load_file
             p = Path(src)
             if p.is_dir():
-                cands = [p / "pytorch_lora_weights.safetensors", p / "model.safetensors"]
+                cands = [p / "pytorch_lora_weights.safetensors", p / "model.safetensors", p / "adapter_model.safetensors"]
                 p = next((c for c in cands if c.exists()), cands[0])
             sd = load_file(str(p)) if p.suffix == ".safetensors" else torch.load(str(p), map_location="cpu")
         self.load_lora_state_dict(sd, alpha=kwargs.get("network_alpha"))
@@ -316,6 +316,26 @@ class UNet2DConditionModel(nn.Module):
 
     def lora_state_dict(self, adapter_name: Optional[str] = None) -> Dict[str, Tensor]:
         return to_peft_state_dict(self._adapters, adapter_name)
+
+    def save_attn_procs(self, save_directory, safe_serialization: bool = True, fmt: str = "diffusers", **kwargs):
+        """diffusers' `UNet2DConditionLoadersMixin.save_attn_procs`: the adapters as `pytorch_lora_weights.safetensors`
+        (`lora.down/up` keys; what train_audioldm_lora.py:577-579 prepares and app.py:11 loads).  fmt="peft_full"
+        writes accelerate's `model.safetensors` instead (generate_audio.py:32)."""
+        if not safe_serialization:
+            raise NotImplementedError("only safetensors checkpoints are written")
+        if self._trainer is not None:
+            self._sync_from_trainer()
+        from .lora import save_lora_checkpoint
+        return save_lora_checkpoint(self._adapters, save_directory, fmt)
+
+    def merged_state_dict(self, scale: float = 1.0) -> Dict[str, Tensor]:
+        """Base weights with the adapters folded in, W' = W + (alpha / r) * scale * B A (peft `merge_and_unload`):
+        `UNet2DConditionModel(arch, unet.merged_state_dict())` is the adapter-free model.  Opt-in only -- the
+        run-time path keeps LoRA unmerged like the reference, and the merged model is not bit-identical to it."""
+        from .lora import merge_lora_into_state_dict
+        if self._trainer is not None:
+            self._sync_from_trainer()
+        return merge_lora_into_state_dict(self._sd, self._adapters, scale)
 
     def custom_attn_processors(self) -> Optional[dict]:
         """{attention path: module} for modules whose processor is not the native one."""
