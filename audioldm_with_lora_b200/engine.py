@@ -84,6 +84,30 @@ class LoraEntry:
         return self.alpha / self.A.shape[0]
 
 
+_PW_SCALARS = ("n_valid", "block_n", "ntaps", "c0", "c1", "c2", "geglu", "ksplit")
+
+
+def _same_layout(a: PackedWeight, b: PackedWeight) -> bool:
+    if a.w.shape != b.w.shape or a.w.device != b.w.device or any(getattr(a, f) != getattr(b, f) for f in _PW_SCALARS):
+        return False
+    for f in ("bias", "ln_g"):
+        ta, tb = getattr(a, f, None), getattr(b, f, None)
+        if (ta is None) != (tb is None) or (ta is not None and ta.shape != tb.shape):
+            return False
+    return True
+
+
+def _overwrite(dst: PackedWeight, src: PackedWeight) -> None:
+    """dst <- src without moving dst's device tensors (same layout, see _same_layout)."""
+    dst.w.copy_(src.w)
+    for f in ("bias", "ln_g"):
+        if getattr(src, f, None) is not None:
+            getattr(dst, f).copy_(getattr(src, f))
+    for f in ("alg_macs_per_row", "lora_fused", "lora_rows"):
+        if hasattr(src, f):
+            setattr(dst, f, getattr(src, f))
+
+
 class UNetEngine:
     def __init__(self, cfg: UNetConfig, state_dict: Dict[str, Tensor], device="cuda"):
         self.cfg = cfg
@@ -242,12 +266,25 @@ class UNetEngine:
         return plan
 
     def _pack_attention(self, plan: dict) -> None:
-        self.weights_version += 1
+        """(Re)pack the attention projections of one plan.  Packed tensors whose shape and tiling are unchanged are
+        overwritten IN PLACE, so device pointers captured in CUDA graphs (the denoising step, the fine-tuning step) and
+        in the trainer's refresh table stay valid; `weights_version` moves only when a pointer did."""
         prev, self._tiling_sms = getattr(self, "_tiling_sms", ops.NUM_SMS), plan.get("sms", getattr(self, "_tiling_sms", ops.NUM_SMS))
+        old = {k: v for k, v in plan["W"].items() if ".attn1." in k or ".attn2." in k}
         try:
             self._pack_attention_impl(plan)
         finally:
             self._tiling_sms = prev
+        W, moved = plan["W"], False
+        for k in [k for k in W if ".attn1." in k or ".attn2." in k]:
+            new, was = W[k], old.pop(k, None)
+            if was is not None and was is not new and _same_layout(was, new):
+                _overwrite(was, new)
+                W[k] = was
+            else:
+                moved = True
+        if moved or old:                  # a tensor was created, resized or dropped
+            self.weights_version += 1
 
     def _pack_attention_impl(self, plan: dict) -> None:
         sd, W, sizes, nb = self.sd, plan["W"], plan["sizes"], plan["nb"]

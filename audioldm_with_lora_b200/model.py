@@ -277,6 +277,7 @@ class UNet2DConditionModel(nn.Module):
         self.engine.set_lora(self._adapters, self.engine.lora_scale)
         if not getattr(self, "_installing_from_trainer", False):
             self._trainer = None             # adapters changed under the trainer: rebuild it on the next grad-mode call
+            self._trainer_synced = None
 
     def add_adapter(self, adapter_config: LoraConfig, adapter_name: str = "default") -> None:
         if adapter_name in self.peft_config:
@@ -291,17 +292,20 @@ class UNet2DConditionModel(nn.Module):
                       adapter_name)
 
     def load_attn_procs(self, pretrained_model_name_or_path_or_dict, **kwargs) -> None:
+        """diffusers' `load_attn_procs` (app.py:11): a state dict, a checkpoint file or a directory holding one.
+        alpha: `network_alpha=` if given, else what `save_attn_procs` / `save_lora_checkpoint` recorded in the file's
+        metadata, else the adapter's rank (scaling 1)."""
         src = pretrained_model_name_or_path_or_dict
+        alpha = kwargs.get("network_alpha")
         if isinstance(src, dict):
-            sd = src
+            self.load_lora_state_dict(src, alpha=alpha)
+            return
+        p = Path(src)
+        if p.is_dir() or p.suffix == ".safetensors":
+            from .lora import load_lora_checkpoint
+            self._install(load_lora_checkpoint(p, alpha=alpha))
         else:
-            from safetensors.torch import load_file
-            p = Path(src)
-            if p.is_dir():
-                cands = [p / "pytorch_lora_weights.safetensors", p / "model.safetensors", p / "adapter_model.safetensors"]
-                p = next((c for c in cands if c.exists()), cands[0])
-            sd = load_file(str(p)) if p.suffix == ".safetensors" else torch.load(str(p), map_location="cpu")
-        self.load_lora_state_dict(sd, alpha=kwargs.get("network_alpha"))
+            self.load_lora_state_dict(torch.load(str(p), map_location="cpu"), alpha=alpha)
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         """peft-keyed LoRA tensors are routed to the adapters; base tensors must match the engine's."""
@@ -315,6 +319,7 @@ class UNet2DConditionModel(nn.Module):
         return type("IncompatibleKeys", (), {"missing_keys": [], "unexpected_keys": unexpected})()
 
     def lora_state_dict(self, adapter_name: Optional[str] = None) -> Dict[str, Tensor]:
+        self._sync_from_trainer()            # the reference checkpoints mid-training (train_audioldm_lora.py:578)
         return to_peft_state_dict(self._adapters, adapter_name)
 
     def save_attn_procs(self, save_directory, safe_serialization: bool = True, fmt: str = "diffusers", **kwargs):
@@ -323,8 +328,7 @@ class UNet2DConditionModel(nn.Module):
         writes accelerate's `model.safetensors` instead (generate_audio.py:32)."""
         if not safe_serialization:
             raise NotImplementedError("only safetensors checkpoints are written")
-        if self._trainer is not None:
-            self._sync_from_trainer()
+        self._sync_from_trainer()
         from .lora import save_lora_checkpoint
         return save_lora_checkpoint(self._adapters, save_directory, fmt)
 
@@ -333,8 +337,7 @@ class UNet2DConditionModel(nn.Module):
         `UNet2DConditionModel(arch, unet.merged_state_dict())` is the adapter-free model.  Opt-in only -- the
         run-time path keeps LoRA unmerged like the reference, and the merged model is not bit-identical to it."""
         from .lora import merge_lora_into_state_dict
-        if self._trainer is not None:
-            self._sync_from_trainer()
+        self._sync_from_trainer()
         return merge_lora_into_state_dict(self._sd, self._adapters, scale)
 
     def custom_attn_processors(self) -> Optional[dict]:
@@ -364,6 +367,7 @@ class UNet2DConditionModel(nn.Module):
                 lin.lora_A[name].weight.requires_grad_(True)
                 lin.lora_B[name].weight.requires_grad_(True)
             self._trainer = tr
+            self._trainer_synced = tr.flat_p.detach().clone()      # built from the adapters just installed: in sync
         return self._trainer
 
     def _trainer_params(self):
@@ -375,21 +379,34 @@ class UNet2DConditionModel(nn.Module):
         return out
 
     def _sync_from_trainer(self) -> None:
+        """Bring `_adapters` and every packed engine plan (all shapes, LayerNorm-folded forms included) up to date with
+        the trainer's flat parameter arena.  The arena is written behind our back -- the reference's loop runs
+        `torch.optim.AdamW` over the peft-shaped Parameters, which are views into it with their own version counters --
+        so the check compares VALUES against a device snapshot of the last sync: one 3.6 MB compare per eval forward /
+        pipeline call / checkpoint, never inside the denoising loop."""
         tr = self._trainer
         if tr is None:
             return
-        key = (tr.step_count, tr.flat_p._version)
-        if key != self._trainer_synced:
-            self._installing_from_trainer = True
-            try:
-                from .engine import LoraEntry
-                ad = {p: LoraEntry(A.detach().float().cpu().clone(), B.detach().float().cpu().clone(),
-                                   tr.slots[p].scaling * tr.slots[p].r) for p, (A, B) in tr.param_views().items()}
-                self._adapters.update(ad)
-                self.engine.set_lora(self._adapters, self.engine.lora_scale)
-            finally:
-                self._installing_from_trainer = False
-            self._trainer_synced = (tr.step_count, tr.flat_p._version)
+        if self._trainer_synced is not None and self._trainer_synced.shape == tr.flat_p.shape and \
+                torch.equal(self._trainer_synced, tr.flat_p):
+            return
+        self._installing_from_trainer = True
+        try:
+            from .engine import LoraEntry
+            host = tr.flat_p.detach().float().cpu()
+            ad = {}
+            for p, s in tr.slots.items():
+                ad[p] = LoraEntry(host[s.off_a: s.off_a + s.r * s.c].view(s.r, s.c).clone(),
+                                  host[s.off_b: s.off_b + s.r * s.c].view(s.c, s.r).clone(), s.scaling * s.r)
+            self._adapters.update(ad)
+            self.engine.set_lora(self._adapters, self.engine.lora_scale)
+        finally:
+            self._installing_from_trainer = False
+        self._trainer_synced = tr.flat_p.detach().clone()
+
+    def sync_adapters(self) -> None:
+        """Public form of the above for callers that drive `unet.engine` directly (AudioLDMPipeline)."""
+        self._sync_from_trainer()
 
     # ------------------------------------------------------------------ forward
     def _sync_engine_lora(self, scale: float) -> None:
@@ -406,8 +423,7 @@ class UNet2DConditionModel(nn.Module):
         if sample.dim() != 4 or sample.shape[1] != self.cfg.in_channels:
             raise ValueError(f"expected sample [B, {self.cfg.in_channels}, H, W], got {tuple(sample.shape)}")
         scale = float((cross_attention_kwargs or {}).get("scale", 1.0))
-        if self.training and torch.is_grad_enabled() and self._adapters and self.b200_device.type == "cuda" and \
-                self.custom_attn_processors() is None:
+        if self.training and torch.is_grad_enabled() and self._adapters and self.custom_attn_processors() is None:
             tr = self.lora_trainer()
             params = self._trainer_params()
             if any(p.requires_grad for p in params):
@@ -437,6 +453,9 @@ class _UNetLoraFunction(torch.autograd.Function):
         t = torch.as_tensor(timestep, dtype=torch.float32, device=dev).reshape(-1)
         t = t.expand(nb).contiguous() if t.numel() == 1 else t.contiguous()
         tr.refresh(nb, h, w)
+        # One activation arena, one outstanding grad-mode forward: a forward whose backward never ran (a validation
+        # loss computed without no_grad, say) is abandoned here, and its backward -- should it come later -- raises.
+        ctx.b200_token = tr.begin_forward()
         xin = torch.zeros(nb, h * w, LATENT_C_PAD, dtype=torch.bfloat16, device=dev)
         ops.pack_nchw_to_nhwc(x, nb, c, h * w, LATENT_C_PAD, xin)
         silu_emb = torch.empty(nb, eng.cfg.temb_channels, dtype=torch.bfloat16, device=dev)
@@ -452,6 +471,10 @@ class _UNetLoraFunction(torch.autograd.Function):
         from .engine import LATENT_C_PAD
         unet, fctx, (nb, h, w) = ctx.b200
         tr = unet._trainer
+        if tr is None or ctx.b200_token != tr.outstanding_forward:
+            raise RuntimeError("B200 UNet backward: the activations of this forward are gone -- a later grad-mode forward "
+                               "(or a change of adapters) reused the activation arena.  Run each grad-mode forward's "
+                               "backward before the next forward, or wrap loss-only forwards in torch.no_grad().")
         deps = tr.arena.alloc((nb * h * w, LATENT_C_PAD), torch.bfloat16)
         deps.zero_()
         ops.pack_nchw_to_nhwc(d_out.detach().to(torch.float32).contiguous(), nb, d_out.shape[1], h * w, LATENT_C_PAD, deps)

@@ -175,6 +175,7 @@ class AudioLDMPipeline:
         """latents NCHW fp32 [B,8,H,W] (already scaled by init_noise_sigma) -> denoised NCHW fp32."""
         eng = self.unet.engine
         sched = self.scheduler
+        self.unet.sync_adapters()            # validation inside a training run (train_audioldm_lora.py:599) sees the trained LoRA
         do_cfg = negative_prompt_embeds is not None
         nb, c, h, w = latents.shape
         sched.set_timesteps(num_inference_steps)
@@ -305,6 +306,7 @@ class AudioLDMPipeline:
                                      negative_prompt_embeds)
         batch = pe.shape[0]
         lat = self.prepare_latents(batch, self.unet.config.in_channels, height, generator, latents)
+        self.unet.sync_adapters()
         self.unet.engine.set_lora_scale(float((cross_attention_kwargs or {}).get("scale", 1.0)))
         lat = self.denoise(lat, pe, ne, num_inference_steps, guidance_scale, eta, callback, callback_steps)
         if output_type == "latent":

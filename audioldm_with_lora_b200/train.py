@@ -101,6 +101,18 @@ class LoraTrainer:
         self._tplans: Dict[Tuple[int, int, int], dict] = {}
         self.arena: Optional[Arena] = None
         self.first_tfm = self._first_adapted_tfm()
+        self._fwd_tokens = 0
+        self.outstanding_forward: Optional[int] = None      # token of the grad-mode forward whose activations are live
+
+    def begin_forward(self) -> int:
+        """Autograd seam: claim the activation arena for a new grad-mode forward.  Activations of a forward whose
+        backward never ran are dropped (the arena is reset); that forward's backward then fails loudly."""
+        if self.outstanding_forward is not None and self.arena is not None:
+            self.arena.live.clear()
+            self.arena.free = [(0, self.arena.buf.numel())]
+        self._fwd_tokens += 1
+        self.outstanding_forward = self._fwd_tokens
+        return self._fwd_tokens
 
     # ------------------------------------------------------------------ bookkeeping
     def _first_adapted_tfm(self) -> str:
@@ -589,6 +601,7 @@ class LoraTrainer:
         self.arena_peak = ar.peak
         ar.live.clear()
         ar.free = [(0, ar.buf.numel())]
+        self.outstanding_forward = None
 
     @staticmethod
     def _first_skip_needing_grad(order, first: int) -> int:
@@ -673,12 +686,16 @@ class LoraTrainer:
         with torch.cuda.graph(g):
             body()
         self._graph = g
+        # the graph holds raw pointers into the engine's packed weights and this trainer's refresh table
+        self._g_version = self.eng.weights_version
 
     def train_step_graphed(self, latents: Tensor, noise: Tensor, timesteps: Tensor, prompt_embeds: Tensor) -> Tensor:
         """train_step with the forward/backward replayed from a CUDA graph.  Returns the loss buffer (a static device
         tensor that the next step overwrites)."""
         nb, _, h, w = latents.shape
-        if getattr(self, "_graph", None) is None or self._g_shape != (nb, h, w):
+        if getattr(self, "_graph", None) is None or self._g_shape != (nb, h, w) or \
+                self._g_version != self.eng.weights_version:
+            self._graph = None
             self.capture(nb, h, w)
         self._g_lat.copy_(latents, non_blocking=True)
         self._g_noise.copy_(noise, non_blocking=True)

@@ -92,6 +92,15 @@ def test_model_save_attn_procs_and_merged_state_dict(tmp_path, weights, fake_ker
     assert set(other.engine.lora) == set(ad)
     p = next(iter(ad))
     assert torch.equal(other._adapters[p].B, ad[p].B) and other._adapters[p].alpha == 4.0
+    # without network_alpha the alpha recorded by save_attn_procs is honoured (alpha != r here: rank 4... alpha 4.0 vs r)
+    r = ad[p].A.shape[0]
+    unet.load_lora_state_dict(b2.to_peft_state_dict(ad), alpha=2.0 * r)
+    unet.save_attn_procs(tmp_path)
+    third = b2.UNet2DConditionModel(TINY, sd, device="cpu")
+    third.load_attn_procs(str(tmp_path))                                   # directory
+    assert third._adapters[p].alpha == 2.0 * r and third.engine.lora[p].scaling == 2.0
+    third.load_attn_procs(str(tmp_path / "pytorch_lora_weights.safetensors"))   # file
+    assert third._adapters[p].alpha == 2.0 * r
     x = synthetic.initial_latents(1, 16)
     pos, _ = synthetic.clap_embeddings(1)
     unmerged = unet.engine.forward(x, 77, pos)
