@@ -298,6 +298,7 @@ def groupnorm_silu_bwd(x0, c0, x1, c1, nb, hw, gamma, beta, stats, silu, dy, dre
         dx1.view(nb, hw, c1).copy_(gx[..., c0:].to(bf16))
 
 
+@torch.enable_grad()          # may run inside an autograd.Function.backward (grad mode off)
 def layernorm_bwd(x, dy, m, c, gamma, eps, dres, dx):
     xr = x.view(m, c).float().requires_grad_(True)
     F.layer_norm(xr, (c,), gamma, torch.zeros_like(gamma), eps).backward(dy.view(m, c).float())
@@ -312,6 +313,7 @@ def geglu_fwd(h, m, f, out):
     return out
 
 
+@torch.enable_grad()          # may run inside an autograd.Function.backward (grad mode off)
 def geglu_bwd(h, dout, m, f, dh):
     hr = h.view(m, 2 * f).float().requires_grad_(True)
     val, gate = hr.chunk(2, -1)
@@ -340,6 +342,7 @@ def zero_insert(dy, nb, h, w, c, z):
     return z
 
 
+@torch.enable_grad()          # may run inside an autograd.Function.backward (grad mode off)
 def upsample_nearest_bwd(dy, nb, h, w, c, ho, wo, dx):
     xr = torch.zeros(nb, c, h, w, requires_grad=True)
     F.interpolate(xr, size=(ho, wo), mode="nearest").backward(dy.view(nb, ho, wo, c).float().permute(0, 3, 1, 2))

@@ -125,6 +125,83 @@ def test_train_step_adamw_and_polynomial_lr(fake_kernels):
     assert polynomial_lr(1000, 1e-5, 100) == pytest.approx(1e-7)
 
 
+def test_eval_checkpoint_and_pipeline_follow_an_external_optimizer(fake_kernels, tmp_path):
+    """the reference-shaped loop (torch AdamW over the peft Parameters, loss.backward()) changes the flat
+    arena behind the model's back.  Every later eval forward, `get_peft_model_state_dict`, `save_attn_procs` and the
+    validation pipeline must see the NEWEST parameters -- train, eval, train, eval."""
+    import torch.nn.functional as F
+    import audioldm_with_lora_b200 as b2
+    from safetensors.torch import load_file
+    unet, _, _ = _tiny(rank=4)
+    unet.requires_grad_(False)
+    tr = unet.lora_trainer()
+    params = [p for p in unet.parameters() if p.requires_grad]
+    assert len(params) == 2 * len(tr.slots)
+    opt = torch.optim.AdamW(params, lr=1e-2)
+    pipe = b2.AudioLDMPipeline(unet, b2.DDIMScheduler(), use_cuda_graph=False)
+    lat_e, _, _, emb_e = _batch(1, 16, seed=5)
+    key = next(k for k in b2.get_peft_model_state_dict(unet) if "lora_B" in k)
+    slot = tr.slots[key.split("base_model.model.")[1].split(".lora_B")[0]]
+    seen_eps, seen_sd, seen_pipe = [], [], []
+    for rnd in range(2):
+        unet.train()
+        lat, noise, t, emb = _batch(2, 16, seed=60 + rnd)
+        pred = unet(lat, t, encoder_hidden_states=None, class_labels=emb, cross_attention_kwargs={"scale": 1.0},
+                    return_dict=False)[0]
+        F.mse_loss(pred.float(), noise.float()).backward()
+        opt.step(); opt.zero_grad()
+        unet.eval()
+        with torch.no_grad():
+            seen_eps.append(unet(lat_e, 300, class_labels=emb_e, return_dict=False)[0].clone())
+        seen_sd.append(b2.get_peft_model_state_dict(unet)[key].clone())
+        f = unet.save_attn_procs(tmp_path / f"ckpt{rnd}")
+        seen_pipe.append(pipe.denoise(lat_e.clone(), emb_e, emb_e.roll(1, 1), 2, 2.5).clone())
+        on_disk = load_file(str(f))
+        assert torch.equal(seen_sd[-1].reshape(-1), tr.flat_p.detach()[slot.off_b: slot.off_b + slot.r * slot.c])
+        assert any(v.numel() == seen_sd[-1].numel() and torch.equal(v.reshape(-1), seen_sd[-1].reshape(-1))
+                   for v in on_disk.values())
+    assert not torch.equal(seen_sd[0], seen_sd[1])
+    assert not torch.equal(seen_eps[0], seen_eps[1])
+    assert not torch.equal(seen_pipe[0], seen_pipe[1])
+
+
+def test_repack_in_place_keeps_device_pointers(fake_kernels):
+    """`engine.set_lora` / `set_lora_scale` on unchanged shapes overwrites the packed tensors in place, so
+    pointers held by captured CUDA graphs and by the trainer's refresh table stay valid and `weights_version` (what
+    `train_step_graphed` and the pipeline key their graphs on) does not move; a wider LoRA segment moves both."""
+    from audioldm_with_lora_b200 import synthetic
+    unet, trainer, _ = _tiny(rank=4)
+    eng = unet.engine
+    plan = eng._plan(2, 16, 16)
+    ptrs = {k: v.w.data_ptr() for k, v in plan["W"].items()}
+    v0 = eng.weights_version
+    p = next(k for k in plan["W"] if k.endswith("attn1.qkv"))
+    before = plan["W"][p].w.clone()
+    eng.set_lora_scale(0.5)
+    assert eng.weights_version == v0 and {k: v.w.data_ptr() for k, v in plan["W"].items()} == ptrs
+    assert not torch.equal(plan["W"][p].w, before)              # ...but the values did change
+    eng.set_lora_scale(1.0)
+    assert torch.equal(plan["W"][p].w, before)
+    lsd = synthetic.random_lora_state_dict(unet.cfg, 40, fmt="peft")       # q,k,v: r_total = 120 > 64: wider K segment
+    unet.load_state_dict(lsd, strict=False)
+    assert eng.weights_version > v0
+
+
+def test_abandoned_grad_mode_forward_fails_loudly(fake_kernels):
+    """two grad-mode forwards before one backward share one activation arena -- the older one's backward
+    must raise instead of reading overwritten activations."""
+    unet, _, _ = _tiny(rank=4)
+    unet.requires_grad_(False)
+    unet.lora_trainer()
+    unet.train()
+    lat, noise, t, emb = _batch(1, 16, seed=3)
+    first = unet(lat, t, class_labels=emb, return_dict=False)[0]
+    second = unet(lat, t, class_labels=emb, return_dict=False)[0]
+    second.float().pow(2).mean().backward()
+    with pytest.raises(RuntimeError, match="activations of this forward are gone"):
+        first.float().pow(2).mean().backward()
+
+
 # ----------------------------------------------------------------------------------------- N > 1: DDP over gloo
 def _ddp_worker(rank, world, port, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
