@@ -78,11 +78,22 @@ groupnorm_silu_kernel(const GnParams p) {
   const __nv_bfloat16* src = from0 ? p.x0 + static_cast<size_t>(n) * p.HW * p.C0 + c
                                    : p.x1 + static_cast<size_t>(n) * p.HW * p.C1 + (c - p.C0);
 
-  // ---- pass 1: per-thread channel sums over this CTA's slab
-  float a[8], b[8];
+  // ---- pass 1: per-thread channel sums over this CTA's slab.  Sums are taken of (x - K_g), K_g = the image's first
+  //      pixel at the group's first channel: E[x^2] - E[x]^2 in fp32 cancels catastrophically when |mean| >> std (real
+  //      activations after a residual add), the shifted form does not (|K_g - mean_g| is of the order of std_g), and
+  //      torch's Welford-style F.group_norm is matched to rounding.  Same pivot in every CTA / lane: the sums add up.
+  auto pivot = [&](int g_abs) -> float {
+    const int gc = g_abs * cpg;
+    const __nv_bfloat16* q = gc < p.C0 ? p.x0 + static_cast<size_t>(n) * p.HW * p.C0 + gc
+                                       : p.x1 + static_cast<size_t>(n) * p.HW * p.C1 + (gc - p.C0);
+    return __bfloat162float(*q);
+  };
+  float a[8], b[8], kv[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = kv[j] = 0.f;
   if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) kv[j] = pivot((c + j) / cpg);
     for (int px = p_begin + lane; px < p_end; px += nlanes * kGnUnroll) {
       uint4 u[kGnUnroll];
 #pragma unroll
@@ -96,8 +107,9 @@ groupnorm_silu_kernel(const GnParams p) {
         unpack8(u[k], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          a[j] += f[j];
-          b[j] = fmaf(f[j], f[j], b[j]);
+          const float d = (px + k * nlanes < p_end) ? f[j] - kv[j] : 0.f;
+          a[j] += d;
+          b[j] = fmaf(d, d, b[j]);
         }
       }
     }
@@ -138,8 +150,9 @@ groupnorm_silu_kernel(const GnParams p) {
   cluster.barrier_arrive();                         // peers may exit once everyone has read their partials
   if (tid < gl) {
     const float cnt = static_cast<float>(p.HW) * cpg;
-    const float mean = s_gpart[64 + 2 * tid] / cnt;
-    const float var = fmaxf(s_gpart[64 + 2 * tid + 1] / cnt - mean * mean, 0.f);
+    const float dm = s_gpart[64 + 2 * tid] / cnt;                    // mean of (x - K_g)
+    const float var = fmaxf(s_gpart[64 + 2 * tid + 1] / cnt - dm * dm, 0.f);
+    const float mean = pivot(blockIdx.z * gl + tid) + dm;
     s_mean[tid] = mean;
     s_rstd[tid] = rsqrtf(var + p.eps);
     if (p.stats != nullptr && rank == 0) {

@@ -289,7 +289,8 @@ def unpack_nhwc_to_nchw(x: Tensor, nb: int, c: int, hw: int, y: Tensor) -> Tenso
 
 def upsample_nearest(x: Tensor, nb: int, h: int, w: int, c: int, ho: int, wo: int, y: Tensor) -> Tensor:
     assert x.dtype == torch.bfloat16 and y.dtype == torch.bfloat16
-    call("b200_upsample_nearest", ptr(x), nb, h, w, c, ho, wo, ptr(y), stream())
+    info = {"desc": f"nb{nb} {h}x{w}->{ho}x{wo} c{c}", "bytes": 2.0 * nb * c * (h * w + ho * wo)} if _lib.PROFILE is not None else None
+    call("b200_upsample_nearest", ptr(x), nb, h, w, c, ho, wo, ptr(y), stream(), info=info)
     return y
 
 
@@ -298,8 +299,11 @@ def sampler_step(eps: Tensor, x: Tensor, x_saved: Optional[Tensor], hist: Option
                  xin_next: Optional[Tensor]) -> None:
     assert eps.dtype == torch.float32 and x.dtype == torch.float32 and table.dtype == torch.float32
     assert step_ptr.dtype == torch.int32
+    # algorithmic bytes: read x, e_u, e_t (fp32), write x' (fp32) and the next CFG-duplicated bf16 UNet input
+    info = {"desc": f"nb{nb} hw{hw}", "bytes": float(nb * hw * c) * ((3 if do_cfg else 2) * 4 + 4 + (2 if do_cfg else 1) * 2)} \
+        if _lib.PROFILE is not None else None
     call("b200_sampler_step", ptr(eps), ptr(x), ptr(x_saved), ptr(hist), ptr(table), ptr(step_ptr), float(guidance),
-         int(do_cfg), nb, hw, c, c_pad, ptr(xin_next), stream())
+         int(do_cfg), nb, hw, c, c_pad, ptr(xin_next), stream(), info=info)
 
 
 def add_noise(x0: Tensor, noise: Tensor, sqrt_ac: Tensor, sqrt_1mac: Tensor, out: Tensor) -> Tensor:

@@ -171,8 +171,10 @@ class AudioLDMPipeline:
     def denoise(self, latents: Tensor, prompt_embeds: Tensor, negative_prompt_embeds: Optional[Tensor],
                 num_inference_steps: int, guidance_scale: float, eta: float = 0.0,
                 callback: Optional[Callable] = None, callback_steps: int = 1,
-                trace: Optional[List[Tensor]] = None) -> Tensor:
-        """latents NCHW fp32 [B,8,H,W] (already scaled by init_noise_sigma) -> denoised NCHW fp32."""
+                trace: Optional[List[Tensor]] = None, step_range: Optional[Tuple[int, int]] = None) -> Tensor:
+        """latents NCHW fp32 [B,8,H,W] (already scaled by init_noise_sigma) -> denoised NCHW fp32.
+        step_range=(first, last): run only steps first .. last-1 of the `num_inference_steps` schedule, `latents` being
+        the state before step `first` (teacher-forced per-step parity checks; DDIM only -- PLMS carries history)."""
         eng = self.unet.engine
         sched = self.scheduler
         self.unet.sync_adapters()            # validation inside a training run (train_audioldm_lora.py:599) sees the trained LoRA
@@ -188,10 +190,15 @@ class AudioLDMPipeline:
             st = self._loops[key] = _LoopState(self, nb, h, w, do_cfg, sched.hist_slots)
         if nsteps > st.table.shape[0]:
             raise ValueError(f"at most {st.table.shape[0]} sampler steps are supported")
+        first, last = (0, nsteps) if step_range is None else (int(step_range[0]), int(step_range[1]))
+        if not 0 <= first <= last <= nsteps:
+            raise ValueError(f"step_range {step_range} outside the {nsteps}-step schedule")
+        if first and sched.hist_slots:
+            raise ValueError("step_range needs a history-free sampler (DDIM)")
         # ---- stage inputs (host -> device copies happen here, inside the caller's timed region)
         st.table[:nsteps].copy_(table.to(self.device), non_blocking=True)
         st.t_steps[:nsteps].copy_(torch.tensor(t_list, dtype=torch.float32).to(self.device), non_blocking=True)
-        st.step.zero_()
+        st.step.fill_(first)
         st.x.copy_(latents.permute(0, 2, 3, 1).reshape(nb, h * w, c))
         xb = st.x.to(torch.bfloat16)
         st.xin[:nb, :, :c] = xb
@@ -216,7 +223,7 @@ class AudioLDMPipeline:
             with torch.cuda.stream(s):
                 saved = (st.x.clone(), st.xin.clone())
                 st.one_step(eng, guidance, overrides, branches)
-                st.step.zero_(); st.x.copy_(saved[0]); st.xin.copy_(saved[1])
+                st.step.fill_(first); st.x.copy_(saved[0]); st.xin.copy_(saved[1])
                 if st.hist is not None:
                     st.hist.zero_()
             torch.cuda.current_stream().wait_stream(s)
@@ -226,7 +233,7 @@ class AudioLDMPipeline:
             st.graph, st.graph_key = g, graph_key
             st.launches_per_step = None
         need_host = callback is not None or trace is not None
-        for i in range(nsteps):
+        for i in range(first, last):
             if self.use_cuda_graph:
                 st.graph.replay()
             else:

@@ -24,6 +24,7 @@ from oracle import pipeline_ref, unet_ref                          # noqa: E402
 from oracle.ddim_ref import DDIMRef, PNDMRef                       # noqa: E402
 
 OUT = Path(__file__).resolve().parent
+TF_STEPS = (0, 1, 2, 5, 10, 25, 50, 100, 150, 199)
 
 
 def main():
@@ -49,6 +50,16 @@ def main():
     with torch.no_grad():
         pipeline_ref.denoise_loop(sd, unet_ref.ARCH_S, p1, n1, x1.clone(), 4, 2.5, lora=lora, trace=trace)
     np.savez_compressed(OUT / "ddim_s_r8_b1_h25_4steps.npz", latents=torch.stack(trace).numpy())
+    # 2b. BASELINE config c2's own latent size: 200 CFG DDIM steps, 1 prompt, latent 250x16 (10 s clip), guidance 2.5.
+    #     Kept: the latent BEFORE step k and AFTER it for k in TF_STEPS (teacher-forced per-step check on the GPU:
+    #     feed `before`, run one step, compare with `after`) and the final latent (free-running drift, log-mel L1).
+    x2 = synthetic.initial_latents(1, 250)
+    trace2 = [x2.clone()]                  # DDIM init_noise_sigma = 1: index k = latent before step k
+    with torch.no_grad():
+        pipeline_ref.denoise_loop(sd, unet_ref.ARCH_S, p1, n1, x2.clone(), 200, 2.5, lora=lora, trace=trace2)
+    keep = sorted({k for s_ in TF_STEPS for k in (s_, s_ + 1)} | {200})
+    np.savez_compressed(OUT / "ddim_s_r8_b1_h250_200steps.npz", index=np.array(keep, dtype=np.int32),
+                        latents=torch.stack([trace2[k] for k in keep]).numpy())
     # 3. scheduler known answers
     s = DDIMRef()
     np.savez_compressed(OUT / "ddim_schedule.npz", alphas_cumprod=s.alphas_cumprod.numpy(),

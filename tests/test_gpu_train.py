@@ -184,3 +184,64 @@ def test_reference_shaped_training_loop_through_autograd():
         lora = unet_ref.LoraSet({p: (A.detach(), B.detach(), al) for p, (A, B, al) in ref.params.items()})
         eps_ref = unet_ref.unet_forward(ref.sd, unet_ref.ARCH_S, lat, 300, emb, lora=lora)
     assert rel(eps, eps_ref) < 3e-2
+
+
+def test_training_then_validation_pipeline_and_checkpoints_see_the_new_adapters(tmp_path):
+    """ADVICE r1 on the device: reference-shaped loop with torch's AdamW (the flat arena changes behind the model's back),
+    then the reference's per-epoch validation (`pipe(...)`, train_audioldm_lora.py:599) and checkpoint
+    (`get_peft_model_state_dict`, :578) -- twice; both must follow the newest parameters.  Peft init (B = 0): before
+    training the adapters have no effect at all, so a stale sync shows up as `pipe == base model`."""
+    import torch.nn.functional as F
+    import audioldm_with_lora_b200 as b2
+    from audioldm_with_lora_b200 import synthetic
+    from audioldm_with_lora_b200.lora import LoraConfig
+    cfg = b2.CONFIGS["S"]
+    unet = b2.UNet2DConditionModel(cfg, synthetic.random_unet_state_dict(cfg, seed=0), device=DEV)
+    b2.get_peft_model(unet, LoraConfig(r=8, lora_alpha=8, target_modules=["to_q", "to_k", "to_v", "to_out.0"]))
+    unet.requires_grad_(False)
+    tr = unet.lora_trainer()
+    opt = torch.optim.AdamW([p for p in unet.parameters() if p.requires_grad], lr=1e-2)
+    pipe = b2.AudioLDMPipeline(unet, b2.DDIMScheduler())
+    x = synthetic.initial_latents(1, 32).to(DEV)
+    pos, neg = [t.to(DEV) for t in synthetic.clap_embeddings(1)]
+    base = pipe.denoise(x.clone(), pos, neg, 2, 2.5).clone()
+    key = next(k for k in b2.get_peft_model_state_dict(unet) if "lora_B" in k)
+    outs, sds = [], []
+    for rnd_ in range(2):
+        unet.train()
+        lat, noise, t, emb = _batch(2, 32, seed=80 + rnd_)
+        pred = unet(lat.to(DEV), t.to(DEV), encoder_hidden_states=None, class_labels=emb.to(DEV), return_dict=False)[0]
+        F.mse_loss(pred.float(), noise.to(DEV).float()).backward()
+        opt.step(); opt.zero_grad()
+        unet.eval()
+        outs.append(pipe.denoise(x.clone(), pos, neg, 2, 2.5).clone())
+        sds.append(b2.get_peft_model_state_dict(unet)[key].clone())
+        s = tr.slots[key.split("base_model.model.")[1].split(".lora_B")[0]]
+        assert torch.equal(sds[-1].reshape(-1), tr.flat_p[s.off_b: s.off_b + s.r * s.c].cpu())
+    assert sds[0].abs().max() > 0 and not torch.equal(sds[0], sds[1])
+    assert rel(outs[0], base) > 1e-4 and not torch.equal(outs[0], outs[1])
+
+
+def test_graphed_step_survives_a_lora_scale_change():
+    """`train_step_graphed` holds raw pointers into the packed weights.  A `set_lora_scale` round trip between
+    steps (validation at another scale) must neither corrupt the next replay (in-place repack keeps pointers) nor be
+    ignored; the graphed loss stays equal to the eager loss on the same batch."""
+    import audioldm_with_lora_b200 as b2
+    from audioldm_with_lora_b200 import synthetic
+    from audioldm_with_lora_b200.train import LoraTrainer
+    cfg = b2.CONFIGS["S"]
+    unet = b2.UNet2DConditionModel(cfg, synthetic.random_unet_state_dict(cfg, seed=0), device=DEV)
+    unet.load_state_dict(synthetic.random_lora_state_dict(cfg, 8, fmt="peft"), strict=False)
+    trainer = LoraTrainer(unet, lr=0.0, weight_decay=0.0)           # lr 0: parameters stay put, losses are comparable
+    lat, noise, t, emb = [v.to(DEV) for v in _batch(2, 32, seed=7)]
+    l0 = trainer.train_step_graphed(lat, noise, t, emb).item()
+    v0, g0 = unet.engine.weights_version, trainer._graph
+    unet.engine.set_lora_scale(0.25)
+    unet.engine.set_lora_scale(1.0)
+    assert unet.engine.weights_version == v0                        # same shapes: overwritten in place
+    l1 = trainer.train_step_graphed(lat, noise, t, emb).item()
+    assert trainer._graph is g0 and abs(l1 - l0) <= 1e-6 * abs(l0)
+    le = trainer.train_step(lat, noise, t, emb).item()
+    assert abs(le - l0) < 1e-3 * abs(l0)
+    unet.load_state_dict(synthetic.random_lora_state_dict(cfg, 24, fmt="peft"), strict=False)   # r_total 72 > 64: repacked
+    assert unet.engine.weights_version != v0
