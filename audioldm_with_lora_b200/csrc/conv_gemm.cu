@@ -34,6 +34,13 @@
 #ifndef B200_GEMM_PROFILE
 #define B200_GEMM_PROFILE 0      // 1: CTA-0 cycle timeline + MMA-thread cost breakdown (B200_GEMM_DEBUG & 4 / & 8)
 #endif
+#ifndef B200_GEMM_LB_THREADS
+// The register budget is set through the thread count promised to ptxas (__maxnreg__ cannot be combined with
+// __launch_bounds__): 352 (the real block size) -> 168 registers per thread = the whole register file for one CTA per SM;
+// 512 -> 128 registers = 44 K of the SM's 64 K, which leaves room for the CTAs of a neighbouring norm / attention kernel
+// in the stream, so programmatic dependent launch can actually overlap prologues and tails.
+#define B200_GEMM_LB_THREADS 352
+#endif
 #ifndef B200_B_EARLY
 #define B200_B_EARLY 1           // 1: the weight producer does not wait for the previous grid (see the PDL note in the kernel)
 #endif
@@ -150,7 +157,7 @@ __device__ __forceinline__ void ln_affine8(float (&v)[8], const float* g, const 
 }
 
 template <bool kCta2, bool kLora = false, bool kLn = false, bool kStat = false>
-__global__ void __launch_bounds__(kThreads, 1)      // 10 warps are allocated as 12: 168 registers per thread at most
+__global__ void __launch_bounds__(B200_GEMM_LB_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmLA,
@@ -969,7 +976,11 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
   const int stage_bytes = kABytes + b_rows * kBlockK * 2;
   const int fixed = kEpiWarps * (kEpiStageBytes + kEpiVecBytes) + 1024 /*align slack*/ + 256 /*barriers*/ +
                     (fused_lora ? kABytes : 0) /*T tile*/;
-  p.stages = (kSmemLimit - fixed) / stage_bytes;
+  // B200_GEMM_SMEM_KB: shared memory this kernel may take (default: all 227 KB).  Less leaves room for the CTAs of the
+  // neighbouring kernels in the stream to become resident early (programmatic dependent launch).
+  static const int smem_cap = getenv("B200_GEMM_SMEM_KB") ? atoi(getenv("B200_GEMM_SMEM_KB")) * 1024 : kSmemLimit;
+  p.stages = ((smem_cap < kSmemLimit ? smem_cap : kSmemLimit) - fixed) / stage_bytes;
+  if (p.stages < 2) p.stages = 2;
   if (p.stages > 8) p.stages = 8;
   static const int dbg_stages = getenv("B200_GEMM_STAGES") ? atoi(getenv("B200_GEMM_STAGES")) : 0;
   static const int dbg_flags = getenv("B200_GEMM_DEBUG") ? atoi(getenv("B200_GEMM_DEBUG")) : 0;

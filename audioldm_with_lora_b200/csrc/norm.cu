@@ -67,6 +67,7 @@ groupnorm_silu_kernel(const GnParams p) {
 
   __shared__ float s_sum[kGnThreads * 8];           // [lane][Cs]
   __shared__ float s_sq[kGnThreads * 8];
+  __shared__ float s_piv[kMaxC];                    // per-channel pivot K_c (this cluster's channel range)
   __shared__ float s_gpart[128];                    // this CTA's per-group {sum, sumsq}; read by cluster peers
   __shared__ float s_mean[32], s_rstd[32];
 
@@ -78,28 +79,27 @@ groupnorm_silu_kernel(const GnParams p) {
   const __nv_bfloat16* src = from0 ? p.x0 + static_cast<size_t>(n) * p.HW * p.C0 + c
                                    : p.x1 + static_cast<size_t>(n) * p.HW * p.C1 + (c - p.C0);
 
-  // ---- pass 1: per-thread channel sums over this CTA's slab.  Sums are taken of (x - K_g), K_g = the image's first
-  //      pixel at the group's first channel: E[x^2] - E[x]^2 in fp32 cancels catastrophically when |mean| >> std (real
-  //      activations after a residual add), the shifted form does not (|K_g - mean_g| is of the order of std_g), and
-  //      torch's Welford-style F.group_norm is matched to rounding.  Same pivot in every CTA / lane: the sums add up.
-  auto pivot = [&](int g_abs) -> float {
-    const int gc = g_abs * cpg;
-    const __nv_bfloat16* q = gc < p.C0 ? p.x0 + static_cast<size_t>(n) * p.HW * p.C0 + gc
-                                       : p.x1 + static_cast<size_t>(n) * p.HW * p.C1 + (gc - p.C0);
-    return __bfloat162float(*q);
-  };
+  // ---- pass 1: per-thread channel sums over this CTA's slab.  Sums are taken of (x - K_c), K_c = the image's first
+  //      pixel in that channel: E[x^2] - E[x]^2 in fp32 cancels catastrophically when |mean| >> std (real activations
+  //      after a residual add); the shifted form does not (|K - mean| is of the order of std) and tracks torch's
+  //      Welford-style F.group_norm to rounding.  Same pivot in every CTA / lane, so partial sums simply add; pixels
+  //      past the slab's end are replaced by the pivot itself (contribute exactly zero: no select in the loop).
   float a[8], b[8], kv[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = b[j] = kv[j] = 0.f;
   if (active) {
+    const uint4 piv_u = *reinterpret_cast<const uint4*>(src);          // pixel 0 of image n, this thread's 8 channels
+    unpack8(piv_u, kv);
+    if (lane == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) kv[j] = pivot((c + j) / cpg);
+      for (int j = 0; j < 8; ++j) s_piv[lc + j] = kv[j];
+    }
     for (int px = p_begin + lane; px < p_end; px += nlanes * kGnUnroll) {
       uint4 u[kGnUnroll];
 #pragma unroll
       for (int k = 0; k < kGnUnroll; ++k) {
         const int pk = px + k * nlanes;
-        u[k] = (pk < p_end) ? *reinterpret_cast<const uint4*>(src + static_cast<size_t>(pk) * ld) : make_uint4(0, 0, 0, 0);
+        u[k] = (pk < p_end) ? *reinterpret_cast<const uint4*>(src + static_cast<size_t>(pk) * ld) : piv_u;
       }
 #pragma unroll
       for (int k = 0; k < kGnUnroll; ++k) {
@@ -107,7 +107,7 @@ groupnorm_silu_kernel(const GnParams p) {
         unpack8(u[k], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float d = (px + k * nlanes < p_end) ? f[j] - kv[j] : 0.f;
+          const float d = f[j] - kv[j];
           a[j] += d;
           b[j] = fmaf(d, d, b[j]);
         }
@@ -132,12 +132,20 @@ groupnorm_silu_kernel(const GnParams p) {
     s_sq[ch] = q;
   }
   __syncthreads();
-  if (tid < 2 * gl) {
-    const int g = tid >> 1;
-    const float* srcv = (tid & 1) ? s_sq : s_sum;
-    float s = 0.f;
-    for (int j = 0; j < cpg; ++j) s += srcv[g * cpg + j];
-    s_gpart[tid] = s;
+  // channels -> groups, re-based on the group's first channel's pivot K_g:
+  //   sum (x - K_g) = s_c + n d,  sum (x - K_g)^2 = q_c + 2 d s_c + n d^2,  d = K_c - K_g, n = pixels of this slab
+  if (tid < gl) {
+    const float npix = static_cast<float>(max(p_end - p_begin, 0));
+    const float kg = s_piv[tid * cpg];
+    float S = 0.f, Q = 0.f;
+    for (int j = 0; j < cpg; ++j) {
+      const int ch = tid * cpg + j;
+      const float d = s_piv[ch] - kg, s = s_sum[ch];
+      S += fmaf(npix, d, s);
+      Q += s_sq[ch] + d * fmaf(npix, d, 2.f * s);
+    }
+    s_gpart[2 * tid] = S;
+    s_gpart[2 * tid + 1] = Q;
   }
   cluster.sync();
   // ---- cluster exchange through DSMEM (fixed rank order)
@@ -152,7 +160,7 @@ groupnorm_silu_kernel(const GnParams p) {
     const float cnt = static_cast<float>(p.HW) * cpg;
     const float dm = s_gpart[64 + 2 * tid] / cnt;                    // mean of (x - K_g)
     const float var = fmaxf(s_gpart[64 + 2 * tid + 1] / cnt - dm * dm, 0.f);
-    const float mean = pivot(blockIdx.z * gl + tid) + dm;
+    const float mean = s_piv[tid * cpg] + dm;
     s_mean[tid] = mean;
     s_rstd[tid] = rsqrtf(var + p.eps);
     if (p.stats != nullptr && rank == 0) {
