@@ -33,6 +33,12 @@ _PROTOS = {
     "b200_conv_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "b200_conv_gemm_gnstat": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
+                                      c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200_gn_stat_slabs": (c_int, [c_int, c_int, c_int]),
+    "b200_groupnorm_apply": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p]),
     "b200_linear_lora": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                  c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "b200_linear_ln": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p,

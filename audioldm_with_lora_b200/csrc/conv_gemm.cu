@@ -108,6 +108,12 @@ struct ConvGemmParams {
   // (sum, sum of squares) of the bf16-rounded values it stores -- fixed slots, no atomics, deterministic.
   float* stat_out;                  // [m_total, stat_chunks, 2] or null
   int stat_chunks;
+  // Producer side of the one-pass GroupNorm (b200_groupnorm_apply): the TMA-store epilogue also leaves, per image, per
+  // 32-pixel slab and per 4-channel unit, the (sum, sum of squares) of the bf16 values it stores -- fixed slots, no
+  // atomics, deterministic.  4 channels nest in every group width of the UNet, so the consumer can regroup them for
+  // any GroupNorm, also one over a concatenation of two tensors.
+  float* gn_stat;                   // [NB, gn_slabs, n_valid / 4, 2] or null
+  int gn_slabs;                     // slabs per image = tiles_h * (W * BH / 32)
 };
 
 // exact-erf GELU to ~2e-7 absolute (Abramowitz-Stegun 7.1.26 erfc; bf16 output rounding is 4e-3 relative):
@@ -156,7 +162,7 @@ __device__ __forceinline__ void ln_affine8(float (&v)[8], const float* g, const 
   v[6] = fmaf(v[6] - mu * g1.z, rs, b1.z); v[7] = fmaf(v[7] - mu * g1.w, rs, b1.w);
 }
 
-template <bool kCta2, bool kLora = false, bool kLn = false, bool kStat = false>
+template <bool kCta2, bool kLora = false, bool kLn = false, bool kStat = false, bool kGn = false>
 __global__ void __launch_bounds__(B200_GEMM_LB_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
@@ -689,6 +695,37 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             tma_store_4d(&tmOut, stage, n_tile * out_cols + cc * 64, q_w, h_t + q_h, n_t + q_n);
             tma_store_commit();
           }
+          if (kGn) {
+            // ---- GroupNorm partial statistics of this warp's 32 rows x 64 columns, read back TRANSPOSED from the staging
+            //      tile (lane l owns columns 2l, 2l+1; the swizzle keeps the 32 lanes on 32 different banks), rows outside the
+            //      image masked, lane pairs combined into 4-channel units
+            const uint32_t valid = __ballot_sync(0xffffffffu, row_ok);
+            const uint32_t tile_a = smem_u32(stage) + ((lane & 3) << 2);
+            const uint32_t ch16 = lane >> 2;
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              uint32_t v;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(tile_a + r * 128 + ((ch16 ^ (r & 7)) << 4)));
+              if ((valid >> r) & 1u) {
+                const float lo = bf16_lo(v), hi = bf16_hi(v);
+                s0 += lo; q0 = fmaf(lo, lo, q0);
+                s1 += hi; q1 = fmaf(hi, hi, q1);
+              }
+            }
+            s0 += s1; q0 += q1;
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+            q0 += __shfl_xor_sync(0xffffffffu, q0, 1);
+            const int rpi = p.W * p.BH;                         // tile rows per image (a multiple of 32: host-checked)
+            const int n_img = n_t + (q * 32) / rpi;
+            const int col = n_tile * out_cols + cc * 64 + 2 * lane;
+            if ((lane & 1) == 0 && col < p.n_valid && n_img < p.NB && m_tile < p.num_m_tiles) {
+              const int spi = rpi >> 5;                         // slabs per (tile, image)
+              const int slab = (m_tile % p.tiles_h) * spi + ((q * 32) % rpi >> 5);
+              reinterpret_cast<float2*>(p.gn_stat)[(static_cast<size_t>(n_img) * p.gn_slabs + slab) * (p.n_valid >> 2) + (col >> 2)] =
+                  make_float2(s0, q0);
+            }
+          }
         }
       } else {
         // -------- fp32 output and/or stride 2: direct 16-byte stores, 32-column groups
@@ -818,7 +855,7 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
                           void* out, int out_ld, int out_fp32, int geglu, int block_n, int max_ctas,
                           int ksplit, float* workspace, int cta_pair, const void* lora_down, int lora_rows, void* t_out,
                           const float* ln_g, const float* ln_ga, const float* ln_ba, float ln_eps, const float* ln_stats,
-                          float* stat_out, void* stream_v);
+                          float* stat_out, void* stream_v, float* gn_stat = nullptr);
 
 // C-ABI: see include/b200ldm.h
 extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, const void* a2, int c2, int nb, int h,
@@ -829,6 +866,28 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
   return conv_gemm_impl(a0, c0, a1, c1, a2, c2, nb, h, w, ntaps, stride, wpacked, n_pad, n_valid, bias, rowvec, rowvec_ld,
                         residual, res_ld, out, out_ld, out_fp32, geglu, block_n, max_ctas, ksplit, workspace, cta_pair,
                         nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, nullptr, stream_v);
+}
+
+// b200_conv_gemm whose epilogue also leaves the partial GroupNorm statistics of its (bf16, stride-1, un-split) output for
+// b200_groupnorm_apply: gn_stat fp32 [nb, slabs, n_valid / 4, 2], slabs = b200_gn_stat_slabs(nb, h, w).
+extern "C" int b200_conv_gemm_gnstat(const void* a0, int c0, const void* a1, int c1, const void* a2, int c2, int nb, int h,
+                                     int w, int ntaps, const void* wpacked, int n_pad, int n_valid, const float* bias,
+                                     const float* rowvec, int rowvec_ld, const void* residual, int res_ld, void* out,
+                                     int out_ld, int block_n, int max_ctas, int cta_pair, float* gn_stat, void* stream_v) {
+  B200_CHECK_ARG(gn_stat != nullptr, "conv_gemm_gnstat: null gn_stat");
+  return conv_gemm_impl(a0, c0, a1, c1, a2, c2, nb, h, w, ntaps, 1, wpacked, n_pad, n_valid, bias, rowvec, rowvec_ld,
+                        residual, res_ld, out, out_ld, 0, 0, block_n, max_ctas, 1, nullptr, cta_pair,
+                        nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, nullptr, stream_v, gn_stat);
+}
+
+// Slabs per image of the statistics b200_conv_gemm_gnstat writes for an [nb, h, w, *] output; 0: this geometry is not
+// supported (a 32-row warp slice of a tile would span two images).
+extern "C" int b200_gn_stat_slabs(int nb, int h, int w) {
+  int BH = 0, BNI = 0;
+  if (pick_box(h, w, nb, &BH, &BNI) != 0) return 0;
+  const int rpi = w * BH;
+  if (rpi % 32 != 0) return 0;
+  return ((h + BH - 1) / BH) * (rpi / 32);
 }
 
 // Linear layer with the rank-r LoRA branch computed INSIDE the kernel (peft lora.Linear, unmerged):
@@ -881,7 +940,7 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
                           void* out, int out_ld, int out_fp32, int geglu, int block_n, int max_ctas,
                           int ksplit, float* workspace, int cta_pair, const void* lora_down, int lora_rows, void* t_out,
                           const float* ln_g, const float* ln_ga, const float* ln_ba, float ln_eps, const float* ln_stats,
-                          float* stat_out, void* stream_v) {
+                          float* stat_out, void* stream_v, float* gn_stat) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const bool fused_lora = lora_down != nullptr;
   const bool fused_ln = ln_g != nullptr;
@@ -964,6 +1023,13 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
     cta_pair = 0;
     p.stat_out = stat_out;
     p.stat_chunks = n_valid / 64;
+  }
+  if (gn_stat) {
+    B200_CHECK_ARG(p.tma_out && ksplit <= 1 && !geglu && n_valid % 4 == 0 && !fused_ln && !fused_lora && !stat_out,
+                   "conv_gemm: gn_stat needs the plain bf16 TMA-store epilogue");
+    B200_CHECK_ARG((w * p.BH) % 32 == 0, "conv_gemm: gn_stat unsupported for %d x %d images (b200_gn_stat_slabs == 0)", h, w);
+    p.gn_stat = gn_stat;
+    p.gn_slabs = p.tiles_h * (w * p.BH / 32);
   }
   int tc = 32;
   while (tc < 2 * block_n + p.lora_n) tc *= 2;
@@ -1053,17 +1119,27 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
     cudaFuncSetAttribute(conv_gemm_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     cudaFuncSetAttribute(conv_gemm_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     cudaFuncSetAttribute(conv_gemm_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaFuncSetAttribute(conv_gemm_kernel<false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaFuncSetAttribute(conv_gemm_kernel<true, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   }
   int grid = p.num_m_groups * p.num_n_tiles * p.ksplit;
   int cap = max_ctas > 0 ? max_ctas : num_sms;
   if (cta2) {
     if (grid > cap / 2) grid = cap / 2;
     if (grid < 1) grid = 1;
-    B200_CHECK_PDL("conv_gemm(2-CTA)", launch_pdl(conv_gemm_kernel<true, false>, dim3(2 * grid), dim3(kThreads), (size_t)smem_bytes,
-                                                  stream, 2, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+    if (gn_stat)
+      B200_CHECK_PDL("conv_gemm_gnstat(2-CTA)", launch_pdl(conv_gemm_kernel<true, false, false, false, true>, dim3(2 * grid),
+                                                           dim3(kThreads), (size_t)smem_bytes, stream, 2, tA[0], tA[1], tA[2], tB,
+                                                           tO, tLA, p));
+    else
+      B200_CHECK_PDL("conv_gemm(2-CTA)", launch_pdl(conv_gemm_kernel<true, false>, dim3(2 * grid), dim3(kThreads), (size_t)smem_bytes,
+                                                    stream, 2, tA[0], tA[1], tA[2], tB, tO, tLA, p));
   } else {
     if (grid > cap) grid = cap;
-    if (stat_out && !fused_ln && fused_lora)
+    if (gn_stat)
+      B200_CHECK_PDL("conv_gemm_gnstat", launch_pdl(conv_gemm_kernel<false, false, false, false, true>, dim3(grid), dim3(kThreads),
+                                                    (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+    else if (stat_out && !fused_ln && fused_lora)
       B200_CHECK_PDL("linear_stats(lora)", launch_pdl(conv_gemm_kernel<false, true, false, true>, dim3(grid), dim3(kThreads),
                                                       (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
     else if (stat_out && !fused_ln)

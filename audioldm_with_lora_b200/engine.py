@@ -41,6 +41,7 @@ class Arena:
         self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
         self.free: List[Tuple[int, int]] = [(0, nbytes)]
         self.live: Dict[int, Tuple[int, int]] = {}
+        self.attached: Dict[int, Tensor] = {}      # side buffers that live and die with a tensor (GroupNorm partial statistics)
         self.peak = 0
 
     def alloc(self, shape, dtype) -> Tensor:
@@ -58,9 +59,15 @@ class Arena:
                 return t
         raise MemoryError(f"b200 arena exhausted allocating {n} bytes")
 
+    def attach(self, t: Tensor, extra: Tensor) -> None:
+        self.attached[t.data_ptr()] = extra
+
     def release(self, t: Optional[Tensor]) -> None:
         if t is None:
             return
+        extra = self.attached.pop(t.data_ptr(), None)
+        if extra is not None:
+            self.release(extra)
         off, n = self.live.pop(t.data_ptr())
         self.free.append((off, n))
         self.free.sort()
@@ -224,7 +231,7 @@ class UNetEngine:
             W[t.name + ".proj_in"] = self._pw([sd[t.name + ".proj_in.weight"][:, :, 0, 0]], sd[t.name + ".proj_in.bias"], mt, 1, c)
             W[t.name + ".proj_out"] = self._pw([sd[t.name + ".proj_out.weight"][:, :, 0, 0]], sd[t.name + ".proj_out.bias"], mt, 1, c)
             W[b + ".ff.net.0.proj"] = self._pw([sd[b + ".ff.net.0.proj.weight"]], sd[b + ".ff.net.0.proj.bias"], mt, 1, c, geglu=True)
-            if ops.LN_FUSED:          # norm3 folded into ff.net.0.proj (engine._Runner.tfm)
+            if ops.ln_fusion_wanted("ff", mt):          # norm3 folded into ff.net.0.proj (engine._Runner.tfm)
                 W[b + ".ff.net.0.proj.ln"] = self._ln_pack(sd[b + ".ff.net.0.proj.weight"], sd[b + ".ff.net.0.proj.bias"],
                                                            sd[b + ".norm3.weight"], sd[b + ".norm3.bias"], mt, c, geglu=True)
             W[b + ".ff.net.2"] = self._pw([sd[b + ".ff.net.2.weight"]], sd[b + ".ff.net.2.bias"], mt, 1, 4 * c)
@@ -315,7 +322,7 @@ class UNetEngine:
                     W[p + ".qkv"] = self._pw([wqkv], None, mt, 1, c)
                 # the same projection with norm1 / norm2 folded in (sampling path)
                 W.pop(p + ".qkv.ln", None); W.pop(p + ".lora_down_qkv.ln", None)
-                if ops.LN_FUSED:
+                if ops.ln_fusion_wanted("qkv", mt):
                     ln = "norm1" if a == "attn1" else "norm2"
                     b_ = f"{t.name}.transformer_blocks.0"
                     gamma, beta = sd[f"{b_}.{ln}.weight"].float(), sd[f"{b_}.{ln}.bias"].float()
@@ -461,7 +468,7 @@ class UNetEngine:
 
     def forward_nhwc(self, xin: Tensor, silu_emb: Tensor, nb: int, h: int, w: int, eps_out: Tensor,
                      taps: Optional[dict] = None, attn_overrides: Optional[dict] = None,
-                     mid_branches: int = 1) -> Tensor:
+                     mid_branches: int = 1, rowvec: Optional[Tensor] = None, rowvec_ready=None) -> Tensor:
         """xin bf16 [nb, h, w, 64] (channels >= 8 zero), silu_emb bf16 [nb, temb_channels]
         -> eps_out fp32 [nb, h*w, 8] (NHWC).
 
@@ -471,7 +478,10 @@ class UNetEngine:
         Measured on B200 (tools/concurrency_probe.py): chains whose kernels together stay under ~148 CTAs overlap
         perfectly (7.0 us per link for 1, 2 or 3 chains); the shallow levels already fill the GPU and stay one chain."""
         prog = self.program()
-        main = _Runner(self, nb, h, w, self._ensure_arena(nb, h, w), silu_emb, taps, attn_overrides)
+        # rowvec (+ rowvec_ready, a CUDA event): the batched time_emb_proj GEMM already computed -- or still being computed
+        # on a side stream (AudioLDMPipeline overlaps the embedding kernels with conv_in); the first ResNet waits for it.
+        main = _Runner(self, nb, h, w, self._ensure_arena(nb, h, w), silu_emb, taps, attn_overrides, rowvec=rowvec)
+        main.rowvec_ready = rowvec_ready
         region = self.middle_region() if (mid_branches > 1 and taps is None and not attn_overrides) else None
         branches = self.effective_branches(nb, mid_branches) if region else 1
         if branches <= 1:
@@ -571,6 +581,7 @@ class _Runner:
             rowvec = arena.alloc((nb, self.plan["temb_total"]), torch.float32)
             ops.conv_gemm(self.W["temb"], silu_emb, 1, nb, 1, rowvec, out_ld=self.plan["temb_total"])
         self.rowvec = rowvec
+        self.rowvec_ready = None
 
     def M(self, lvl: int) -> int:
         return self.nb * self.sizes[lvl][0] * self.sizes[lvl][1]
@@ -594,6 +605,12 @@ class _Runner:
     def gn(self, x0, c0, x1, c1, lvl, name, eps, silu):
         hh, ww = self.sizes[lvl]
         y = self.ar.alloc((self.M(lvl), c0 + c1), torch.bfloat16)
+        st0 = self.ar.attached.get(x0.data_ptr())
+        st1 = self.ar.attached.get(x1.data_ptr()) if x1 is not None else None
+        if st0 is not None and (x1 is None or st1 is not None) and ((c0 + c1) // self.cfg.groups) % 4 == 0:
+            # one pass: the producers' epilogues left the partial statistics (b200_conv_gemm_gnstat)
+            return ops.groupnorm_apply(x0, c0, st0, x1, c1, st1, self.nb, hh * ww, self.S[name + ".weight"],
+                                       self.S[name + ".bias"], eps, silu, y, self.cfg.groups)
         return ops.groupnorm_silu(x0, c0, x1, c1, self.nb, hh * ww, self.S[name + ".weight"], self.S[name + ".bias"], eps,
                                   silu, y, self.cfg.groups)
 
@@ -602,23 +619,46 @@ class _Runner:
             return self.ar.alloc((pw.ksplit * self.M(lvl) * pw.n_pad,), torch.float32)
         return None
 
-    def conv(self, name, a0, lvl, *, a1=None, a2=None, rowvec_off=None, residual=None, stride=1, out=None, out_lvl=None):
+    def _gn_stat(self, pw, out, lvl, stride=1):
+        """Partial-statistics buffer for an output that a GroupNorm will read (attached to `out`: released with it), or
+        None where the producing launch cannot leave them (split-K, stride 2, fp32, borrowed output, tiny images)."""
+        if not ops.GN_ONEPASS:
+            return None
+        hh, ww = self.sizes[lvl]
+        slabs = ops.gn_stat_slabs(self.nb, hh, ww)
+        if (pw.ksplit > 1 or stride != 1 or out.dtype != torch.bfloat16 or slabs <= 0 or pw.n_valid % 4 or pw.block_n % 64
+                or pw.geglu or out.data_ptr() not in self.ar.live):
+            return None
+        st = self.ar.alloc((self.nb, slabs, pw.n_valid // 4, 2), torch.float32)
+        self.ar.attach(out, st)
+        return st
+
+    def conv(self, name, a0, lvl, *, a1=None, a2=None, rowvec_off=None, residual=None, stride=1, out=None, out_lvl=None,
+             gn_next=False):
         pw = self.W[name]
         hh, ww = self.sizes[lvl]
         if out is None:
             out = self.ar.alloc((self.M(out_lvl if out_lvl is not None else lvl), pw.n_valid), torch.bfloat16)
         rv = self.rowvec[:, rowvec_off:] if rowvec_off is not None else None
         ws = self._ws(pw, lvl, stride, out.dtype == torch.float32)
+        st = self._gn_stat(pw, out, lvl, stride) if gn_next else None
         ops.conv_gemm(pw, a0, self.nb, hh, ww, out, a1=a1, a2=a2, stride=stride, rowvec=rv,
-                      rowvec_ld=self.plan["temb_total"], residual=residual, workspace=ws, max_ctas=self.max_ctas)
+                      rowvec_ld=self.plan["temb_total"], residual=residual, workspace=ws, max_ctas=self.max_ctas, gn_stat=st)
         self.ar.release(ws)
         return out
 
-    def linear(self, name, a0, lvl, *, a1=None, residual=None):
+    def linear(self, name, a0, lvl, *, a1=None, residual=None, gn_next=False):
+        """gn_next: the output is a feature map a GroupNorm reads next (Transformer2DModel.proj_out): run it with the
+        level's image geometry so the epilogue can leave per-image statistics (a 1x1 conv is the same GEMM)."""
         pw = self.W[name]
         out = self.ar.alloc((self.M(lvl), pw.n_valid), torch.bfloat16)
         ws = self._ws(pw, lvl)
-        ops.conv_gemm(pw, a0, 1, self.M(lvl), 1, out, a1=a1, residual=residual, workspace=ws, max_ctas=self.max_ctas)
+        st = self._gn_stat(pw, out, lvl) if gn_next else None
+        if st is not None:
+            hh, ww = self.sizes[lvl]
+            ops.conv_gemm(pw, a0, self.nb, hh, ww, out, a1=a1, residual=residual, max_ctas=self.max_ctas, gn_stat=st)
+        else:
+            ops.conv_gemm(pw, a0, 1, self.M(lvl), 1, out, a1=a1, residual=residual, workspace=ws, max_ctas=self.max_ctas)
         self.ar.release(ws)
         return out
 
@@ -649,14 +689,14 @@ class _Runner:
     def resnet(self, r: ResnetDesc, x0, x1, lvl):
         c_h = r.cin - r.skip_c
         n1 = self.gn(x0, c_h, x1, r.skip_c, lvl, r.name + ".norm1", 1e-5, True)
-        h1 = self.conv(r.name + ".conv1", n1, lvl, rowvec_off=self.plan["temb_off"][r.name])
+        h1 = self.conv(r.name + ".conv1", n1, lvl, rowvec_off=self.plan["temb_off"][r.name], gn_next=True)
         self.ar.release(n1)
         n2 = self.gn(h1, r.cout, None, 0, lvl, r.name + ".norm2", 1e-5, True)
         self.ar.release(h1)
         if r.has_shortcut:
-            out = self.conv(r.name + ".conv2", n2, lvl, a1=x0, a2=x1)
+            out = self.conv(r.name + ".conv2", n2, lvl, a1=x0, a2=x1, gn_next=True)
         else:
-            out = self.conv(r.name + ".conv2", n2, lvl, residual=x0)
+            out = self.conv(r.name + ".conv2", n2, lvl, residual=x0, gn_next=True)
         self.ar.release(n2)
         return out
 
@@ -747,7 +787,7 @@ class _Runner:
             ar.release(ln)
         new_tok = self.linear(b + ".ff.net.2", ffh, lvl, residual=tok)
         ar.release(ffh); ar.release(tok)
-        out = self.linear(t.name + ".proj_out", new_tok, lvl, residual=x)
+        out = self.linear(t.name + ".proj_out", new_tok, lvl, residual=x, gn_next=True)
         ar.release(new_tok)
         return out
 
@@ -762,13 +802,16 @@ class _Runner:
         for k, st in enumerate(steps):
             kind = st[0]
             if kind == "conv_in":
-                hcur = self.conv("conv_in", xin, 0)
+                hcur = self.conv("conv_in", xin, 0, gn_next=True)
                 self.tap("conv_in", hcur, 0, cfg.block_out_channels[0])
             elif kind == "push":
                 skips.append((hcur, st[1]))
                 on_stack.add(hcur.data_ptr())
             elif kind == "res":
                 _, r, lvl, pops = st
+                if self.rowvec_ready is not None:          # join the side stream that computes the embedding projections
+                    torch.cuda.current_stream().wait_event(self.rowvec_ready)
+                    self.rowvec_ready = None
                 sk = None
                 if pops:
                     sk, _ = skips.pop()
@@ -802,7 +845,7 @@ class _Runner:
                 up = self.ar.alloc((self.M(lvl - 1), c), torch.bfloat16)
                 ops.upsample_nearest(hcur, self.nb, hs, ws_, c, ho, wo, up)
                 self.rel(hcur)
-                hcur = self.conv(name, up, lvl - 1, out=final_out if k == last else None)
+                hcur = self.conv(name, up, lvl - 1, out=final_out if k == last else None, gn_next=True)
                 self.ar.release(up)
             elif kind == "out":
                 n = self.gn(hcur, cfg.block_out_channels[0], None, 0, 0, "conv_norm_out", 1e-5, True)

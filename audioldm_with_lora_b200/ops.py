@@ -123,8 +123,11 @@ def choose_tiling(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_
 def conv_gemm(pw: PackedWeight, a0: Tensor, nb: int, h: int, w: int, out: Tensor, *, a1: Optional[Tensor] = None,
               a2: Optional[Tensor] = None, stride: int = 1, rowvec: Optional[Tensor] = None, rowvec_ld: int = 0,
               residual: Optional[Tensor] = None, out_ld: Optional[int] = None, max_ctas: int = 0,
-              workspace: Optional[Tensor] = None, cta_pair: Optional[bool] = None) -> Tensor:
-    """out[pix, :n_valid] = epilogue(implicit GEMM); see include/b200ldm.h::b200_conv_gemm."""
+              workspace: Optional[Tensor] = None, cta_pair: Optional[bool] = None,
+              gn_stat: Optional[Tensor] = None) -> Tensor:
+    """out[pix, :n_valid] = epilogue(implicit GEMM); see include/b200ldm.h::b200_conv_gemm.
+    gn_stat (fp32 [nb, gn_stat_slabs(nb, h, w), n_valid / 4, 2]): also leave the partial GroupNorm statistics of the
+    output for groupnorm_apply (b200_conv_gemm_gnstat)."""
     assert a0.dtype == torch.bfloat16 and a0.is_contiguous()
     assert a0.numel() == nb * h * w * pw.c0, (a0.shape, nb, h, w, pw.c0)
     if pw.c1:
@@ -146,11 +149,49 @@ def conv_gemm(pw: PackedWeight, a0: Tensor, nb: int, h: int, w: int, out: Tensor
         m_out = nb * h * w if stride == 1 else nb * ((h - 1) // 2 + 1) * ((w - 1) // 2 + 1)
         info = {"flops": 2.0 * m_out * pw.macs_per_row, "m": nb * h * w, "n": pw.n_valid,
                 "k": pw.k, "bn": pw.block_n, "taps": pw.ntaps, "desc": f"ks{ksplit}" if ksplit > 1 else None}
+    pair = (int(CTA_PAIR and pw.block_n >= PAIR_MIN_BN) if cta_pair is None else (2 if cta_pair else 0))
+    if gn_stat is not None:
+        assert stride == 1 and not out_fp32 and ksplit == 1 and not pw.geglu and gn_stat.dtype == torch.float32
+        assert gn_stat.numel() == nb * gn_stat_slabs(nb, h, w) * (pw.n_valid // 4) * 2 and gn_stat.numel() > 0
+        if info is not None:
+            info["desc"] = "gnstat"
+        call("b200_conv_gemm_gnstat", ptr(a0), pw.c0, ptr(a1) if pw.c1 else None, pw.c1, ptr(a2) if pw.c2 else None, pw.c2,
+             nb, h, w, pw.ntaps, ptr(pw.w), pw.n_pad, pw.n_valid, ptr(pw.bias), ptr(rowvec), rowvec_ld, ptr(residual), res_ld,
+             ptr(out), ld, pw.block_n, max_ctas, pair, ptr(gn_stat), stream(), info=info)
+        return out
     call("b200_conv_gemm", ptr(a0), pw.c0, ptr(a1) if pw.c1 else None, pw.c1, ptr(a2) if pw.c2 else None, pw.c2,
          nb, h, w, pw.ntaps, stride, ptr(pw.w), pw.n_pad, pw.n_valid, ptr(pw.bias), ptr(rowvec), rowvec_ld,
          ptr(residual), res_ld, ptr(out), ld, int(out_fp32), int(pw.geglu), pw.block_n, max_ctas, ksplit,
-         ptr(workspace) if ksplit > 1 else None, (int(CTA_PAIR and pw.block_n >= PAIR_MIN_BN) if cta_pair is None else (2 if cta_pair else 0)), stream(), info=info)
+         ptr(workspace) if ksplit > 1 else None, pair, stream(), info=info)
     return out
+
+
+# GroupNorm statistics from the producing conv's epilogue + a one-pass apply kernel.  Parity-tested, but measured on B200
+# it does not pay: the transposed read-back costs the producer ~1.2 us on its critical path, about
+# what the consumer saves.  Opt-in.
+GN_ONEPASS = os.environ.get("B200_GN_ONEPASS", "0") != "0"
+_SLABS: dict = {}
+
+
+def gn_stat_slabs(nb: int, h: int, w: int) -> int:
+    """Slabs per image of the GroupNorm partial statistics a conv over [nb, h, w, *] leaves (0: unsupported geometry)."""
+    key = (nb, h, w)
+    if key not in _SLABS:
+        _SLABS[key] = int(_lib.load().b200_gn_stat_slabs(nb, h, w))
+    return _SLABS[key]
+
+
+def groupnorm_apply(x0: Tensor, c0: int, st0: Tensor, x1: Optional[Tensor], c1: int, st1: Optional[Tensor], nb: int, hw: int,
+                    gamma: Tensor, beta: Tensor, eps: float, silu: bool, y: Tensor, groups: int = 32) -> Tensor:
+    """One-pass GroupNorm (+SiLU) over cat(x0, x1) from the producers' partial statistics; see b200_groupnorm_apply."""
+    assert x0.dtype == torch.bfloat16 and y.dtype == torch.bfloat16 and st0.dtype == torch.float32
+    assert gamma.numel() == c0 + c1 and gamma.dtype == torch.float32
+    slabs0 = st0.numel() // (nb * (c0 // 4) * 2)
+    slabs1 = st1.numel() // (nb * (c1 // 4) * 2) if c1 else 0
+    info = {"desc": f"nb{nb} hw{hw} c{c0}+{c1}", "bytes": 4.0 * nb * hw * (c0 + c1)} if _lib.PROFILE is not None else None
+    call("b200_groupnorm_apply", ptr(x0), c0, ptr(st0), slabs0, ptr(x1) if c1 else None, c1, ptr(st1) if c1 else None, slabs1,
+         nb, hw, groups, ptr(gamma), ptr(beta), float(eps), int(silu), ptr(y), stream(), info=info)
+    return y
 
 
 LORA_FUSED = os.environ.get("B200_LORA_FUSED", "1") != "0"
@@ -192,6 +233,15 @@ def linear_lora(pw: PackedWeight, down: PackedWeight, x: Tensor, m: int, out: Te
 # per step, but measured on B200 it does not pay yet: 5.36 vs 5.25 ms per step (the folded level-1 QKV GEMM needs
 # 192-wide tiles for the in-kernel LoRA branch and loses more than the LayerNorm launch cost).  Opt-in.
 LN_FUSED = os.environ.get("B200_LN_FUSED", "0") != "0"
+# Selective form: fold a LayerNorm only where the layer has at most this many 128-row m-tiles (the deep UNet levels are
+# launch-latency-bound, the shallow ones pay for the 192-column tile cap).  -1: no limit (everything when LN_FUSED).
+LN_FUSED_QKV_MAX_MT = int(os.environ.get("B200_LN_FUSED_QKV_MT", "-1"))     # norm1 / norm2 -> the QKV GEMM
+LN_FUSED_FF_MAX_MT = int(os.environ.get("B200_LN_FUSED_FF_MT", "-1"))       # norm3 -> ff.net.0.proj (GEGLU)
+
+
+def ln_fusion_wanted(kind: str, m_tiles: int) -> bool:
+    lim = LN_FUSED_QKV_MAX_MT if kind == "qkv" else LN_FUSED_FF_MAX_MT
+    return LN_FUSED and (lim < 0 or m_tiles <= lim)
 
 
 def linear_stats(pw: PackedWeight, x: Tensor, m: int, out: Tensor, stat_out: Tensor, *, a1: Optional[Tensor] = None,

@@ -56,11 +56,30 @@ class _LoopState:
         self.guidance = 1.0
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_key = None
+        # the timestep / class embedding and the batched time_emb_proj GEMM do not depend on the latents: they run on a
+        # side stream (a parallel branch of the step graph) next to conv_in and the first GroupNorm
+        self.overlap_embed = dev.type == "cuda" and os.environ.get("B200_EMBED_OVERLAP", "1") != "0"
+        self.side = torch.cuda.Stream(device=dev) if self.overlap_embed else None
+        self.rowvec: Optional[Tensor] = None
 
     def one_step(self, eng, guidance: float, overrides=None, branches: int = 1) -> None:
-        eng.embed(self.t_steps, self.step, False, self.labels, None, self.silu_emb)
-        eng.forward_nhwc(self.xin, self.silu_emb, self.nb_unet, self.h, self.w, self.eps, attn_overrides=overrides,
-                         mid_branches=branches)
+        if self.overlap_embed:
+            plan = eng._plan(self.nb_unet, self.h, self.w)
+            if self.rowvec is None or self.rowvec.shape[1] != plan["temb_total"]:
+                self.rowvec = torch.zeros(self.nb_unet, plan["temb_total"], dtype=torch.float32, device=self.xin.device)
+            cur = torch.cuda.current_stream()
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                eng.embed(self.t_steps, self.step, False, self.labels, None, self.silu_emb)
+                ops.conv_gemm(plan["W"]["temb"], self.silu_emb, 1, self.nb_unet, 1, self.rowvec, out_ld=plan["temb_total"])
+                ready = torch.cuda.Event()
+                ready.record(self.side)
+            eng.forward_nhwc(self.xin, self.silu_emb, self.nb_unet, self.h, self.w, self.eps, attn_overrides=overrides,
+                             mid_branches=branches, rowvec=self.rowvec, rowvec_ready=ready)
+        else:
+            eng.embed(self.t_steps, self.step, False, self.labels, None, self.silu_emb)
+            eng.forward_nhwc(self.xin, self.silu_emb, self.nb_unet, self.h, self.w, self.eps, attn_overrides=overrides,
+                             mid_branches=branches)
         ops.sampler_step(self.eps, self.x, self.x_saved, self.hist, self.table, self.step, guidance, self.do_cfg,
                          self.nb_lat, self.h * self.w, eng.cfg.in_channels, LATENT_C_PAD, self.xin)
 

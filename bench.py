@@ -513,7 +513,10 @@ def main():
     tp = ROOT / "profiles" / "conv_gemm_ncu_traffic.json"        # dram bytes of one profiled launch (ncu --set full)
     if tp.exists():
         traffic = json.loads(tp.read_text())
-    cg = by.get("b200_conv_gemm", {"ms": 0.0, "calls": 0, "flops": 0.0})
+    cg = {"ms": 0.0, "calls": 0, "flops": 0.0}
+    for k_ in ("b200_conv_gemm", "b200_conv_gemm_gnstat"):      # the same kernel; the second entry point also leaves GroupNorm partials
+        for f_ in cg:
+            cg[f_] += by.get(k_, {}).get(f_, 0)
     total_ms = sum(d["ms"] for d in by.values()) or 1.0
     achieved = cg["flops"] / (cg["ms"] / 1e3) / 1e12 if cg["ms"] else 0.0
     unet_flops = 101.74e9 * 2 * BATCH
@@ -533,7 +536,7 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: all conv/linear layers)",
                      "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                      "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
-                     "how": f"sum of algorithmic FLOPs of the step's {cg['calls']} b200_conv_gemm launches (every conv / linear layer "
+                     "how": f"sum of algorithmic FLOPs of the step's {cg['calls']} b200_conv_gemm / b200_conv_gemm_gnstat launches (every conv / linear layer "
                             "except the LoRA-adapted projections, which run in b200_linear_lora) / sum of their per-launch "
                             "device times (each launch replayed 8x in its own CUDA graph, CUDA events on the launching stream)",
                      "launches_per_step": cg["calls"], "ms_per_step": cg["ms"], "share_of_step": cg["ms"] / total_ms,
@@ -553,7 +556,7 @@ def main():
                           "ms_per_step": round(by[k]["ms"], 4), "achieved": round(by[k]["bytes"] / (by[k]["ms"] / 1e3) / 1e9, 1),
                           "peak": hbm, "unit": "GB/s", "frac": round(by[k]["bytes"] / (by[k]["ms"] / 1e3) / 1e9 / hbm, 4),
                           "bytes_are": "algorithmic: one read + one write of the tensor (GroupNorm's second read is an L2 hit)"}
-                         for k in ("b200_groupnorm_silu", "b200_layernorm", "b200_sampler_step", "b200_upsample_nearest")
+                         for k in ("b200_groupnorm_apply", "b200_groupnorm_silu", "b200_layernorm", "b200_sampler_step", "b200_upsample_nearest")
                          if k in by and by[k]["bytes"] and by[k]["ms"]],
         "extra_configs": extra,
     }

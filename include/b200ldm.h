@@ -54,6 +54,19 @@ int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, const void* a
                    int out_fp32, int geglu, int block_n, int max_ctas, int ksplit, float* workspace, int cta_pair,
                    void* stream);
 
+/* b200_conv_gemm (bf16 output, stride 1, no split-K, no GEGLU) whose epilogue ALSO leaves the partial GroupNorm statistics
+ * of the tensor it stores, for the one-pass b200_groupnorm_apply that consumes it: gn_stat fp32
+ * [nb, slabs, n_valid / 4, 2] = per image, per 32-pixel slab of a tile and per 4-channel unit the (sum, sum of squares) of
+ * the stored bf16 values; slabs = b200_gn_stat_slabs(nb, h, w) (0: geometry unsupported).  Fixed slots, no atomics:
+ * deterministic.  Every GroupNorm input of the UNet is the output of such a layer (ResnetBlock2D.conv1 / conv2,
+ * Transformer2DModel.proj_out, Upsample2D.conv, conv_in -- diffusers, via train_audioldm_lora.py:539-546), so
+ * F.group_norm's statistics pass over the activation disappears. */
+int b200_conv_gemm_gnstat(const void* a0, int c0, const void* a1, int c1, const void* a2, int c2, int nb, int h, int w,
+                          int ntaps, const void* wpacked, int n_pad, int n_valid, const float* bias, const float* rowvec,
+                          int rowvec_ld, const void* residual, int res_ld, void* out, int out_ld, int block_n,
+                          int max_ctas, int cta_pair, float* gn_stat, void* stream);
+int b200_gn_stat_slabs(int nb, int h, int w);
+
 /* Linear layer with the rank-r LoRA branch computed inside the kernel (peft lora.Linear, unmerged; LoRA config at
  * generate_audio.py:21-29, train_audioldm_lora.py:378-385):  out = x W^T + (x A^T)(s B)^T (+ bias + residual).
  * Phase 0 of every tile runs T = x A^T as a second, narrow tcgen05.mma into spare TMEM columns; the epilogue warps turn
@@ -96,6 +109,13 @@ int b200_set_sm_budget(int n);
 int b200_groupnorm_silu(const void* x0, int c0, const void* x1, int c1, int nb, int hw, int groups,
                         const float* gamma, const float* beta, float eps, int silu, void* y,
                         void* stream);
+
+/* One-pass GroupNorm (+SiLU) over cat(x0, x1): the group statistics are merged (fp64) from the partials the producers
+ * left (b200_conv_gemm_gnstat: st0 [nb, slabs0, c0 / 4, 2], st1 [nb, slabs1, c1 / 4, 2]), then the tensor is streamed
+ * once.  No cluster, no second read.  Same result contract as b200_groupnorm_silu. */
+int b200_groupnorm_apply(const void* x0, int c0, const float* st0, int slabs0, const void* x1, int c1, const float* st1,
+                         int slabs1, int nb, int hw, int groups, const float* gamma, const float* beta, float eps,
+                         int silu, void* y, void* stream);
 
 /* LayerNorm over the last dim of a [m, c] bf16 matrix.  Replaces F.layer_norm in
  * BasicTransformerBlock.norm1/2/3 (diffusers, via train_audioldm_lora.py:539-546). */

@@ -20,7 +20,7 @@ def _store(out, val, n_valid, ld=None):
 
 
 def conv_gemm(pw, a0, nb, h, w, out, *, a1=None, a2=None, stride=1, rowvec=None, rowvec_ld=0, residual=None,
-              out_ld=None, max_ctas=0, workspace=None, cta_pair=None):
+              out_ld=None, max_ctas=0, workspace=None, cta_pair=None, gn_stat=None):
     M = nb * h * w
     x = a0.view(nb, h, w, pw.c0).float()
     cols = []
@@ -51,7 +51,46 @@ def conv_gemm(pw, a0, nb, h, w, out, *, a1=None, a2=None, stride=1, rowvec=None,
     if residual is not None:
         acc = acc + residual.reshape(acc.shape[0], -1)[:, :pw.n_valid].float()
     _store(out, acc, pw.n_valid, out_ld)
+    if gn_stat is not None:
+        # b200_conv_gemm_gnstat: per image / 32-pixel slab of a tile / 4-channel unit (sum, sum of squares) of the STORED values
+        from audioldm_with_lora_b200.ops import box_rows
+        assert stride == 1 and out.dtype == torch.bfloat16
+        bh, _ = box_rows(h, w, nb)
+        spi = w * bh // 32
+        v = out.view(nb, h, w, -1)[..., :pw.n_valid].float().reshape(nb, h, w, pw.n_valid // 4, 4)
+        hh = torch.arange(h).view(h, 1).expand(h, w)
+        ww = torch.arange(w).view(1, w).expand(h, w)
+        slab = ((hh // bh) * spi + ((hh % bh) * w + ww) // 32).reshape(-1)
+        st = gn_stat.view(nb, -1, pw.n_valid // 4, 2)
+        st.zero_()
+        flat = v.reshape(nb, h * w, pw.n_valid // 4, 4)
+        st[..., 0].index_add_(1, slab, flat.sum(-1))
+        st[..., 1].index_add_(1, slab, (flat * flat).sum(-1))
     return out
+
+
+def gn_stat_slabs(nb, h, w):
+    from audioldm_with_lora_b200.ops import box_rows
+    bh, _ = box_rows(h, w, nb)
+    return ((h + bh - 1) // bh) * (w * bh // 32) if (w * bh) % 32 == 0 else 0
+
+
+def groupnorm_apply(x0, c0, st0, x1, c1, st1, nb, hw, gamma, beta, eps, silu, y, groups=32):
+    c = c0 + c1
+    s = st0.view(nb, -1, c0 // 4, 2).double().sum(1)
+    if c1:
+        s = torch.cat([s, st1.view(nb, -1, c1 // 4, 2).double().sum(1)], 1)
+    g = s.view(nb, groups, c // 4 // groups, 2).sum(2)
+    cnt = hw * (c // groups)
+    mean = g[..., 0] / cnt
+    var = (g[..., 1] / cnt - mean * mean).clamp_min(0)
+    x = torch.cat([x0.view(nb, hw, c0)] + ([x1.view(nb, hw, c1)] if c1 else []), -1).float()
+    xn = (x.view(nb, hw, groups, -1) - mean.float()[:, None, :, None]) * torch.rsqrt(var.float() + eps)[:, None, :, None]
+    out = xn.view(nb, hw, c) * gamma + beta
+    if silu:
+        out = F.silu(out)
+    y.copy_(out.view(y.shape).to(y.dtype))
+    return y
 
 
 def set_sm_budget(n):
@@ -386,5 +425,5 @@ def install(monkeypatch, ops_module):
     """Replace the kernel wrappers of `ops_module` (keeps PackedWeight / tiling helpers)."""
     for name in ("conv_gemm", "groupnorm_silu", "layernorm", "attention", "time_class_embed",
                  "pack_nchw_to_nhwc", "unpack_nhwc_to_nchw", "upsample_nearest", "sampler_step", "add_noise",
-                 "adamw_flat", "mse_partial", "set_sm_budget", "linear_lora_ok", "linear_lora", "linear_ln", "linear_stats") + TRAIN_OPS:
+                 "adamw_flat", "mse_partial", "set_sm_budget", "gn_stat_slabs", "groupnorm_apply", "linear_lora_ok", "linear_lora", "linear_ln", "linear_stats") + TRAIN_OPS:
         monkeypatch.setattr(ops_module, name, globals()[name])

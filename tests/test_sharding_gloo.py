@@ -32,7 +32,7 @@ def _denoise_shard(rank, world, n_prompts, steps):
     from audioldm_with_lora_b200.sharding import shard_prompts
     from tests import fake_ops
     for name in ("conv_gemm", "groupnorm_silu", "layernorm", "attention", "time_class_embed", "pack_nchw_to_nhwc",
-                 "unpack_nhwc_to_nchw", "upsample_nearest", "sampler_step", "set_sm_budget", "linear_lora_ok", "linear_lora", "linear_ln", "linear_stats"):
+                 "unpack_nhwc_to_nchw", "upsample_nearest", "sampler_step", "set_sm_budget", "gn_stat_slabs", "groupnorm_apply", "linear_lora_ok", "linear_lora", "linear_ln", "linear_stats"):
         setattr(ops, name, getattr(fake_ops, name))
     tiny = UNetConfig("tiny", (64, 128, 192, 256))
     unet = b2.UNet2DConditionModel(tiny, synthetic.random_unet_state_dict(tiny, seed=0), device="cpu")

@@ -17,7 +17,7 @@ def _install_fakes():
     from audioldm_with_lora_b200 import ops
     from tests import fake_ops
     for name in ("conv_gemm", "groupnorm_silu", "layernorm", "attention", "time_class_embed", "pack_nchw_to_nhwc",
-                 "unpack_nhwc_to_nchw", "upsample_nearest", "sampler_step", "set_sm_budget", "linear_lora_ok", "linear_lora", "linear_ln", "linear_stats", "add_noise", "adamw_flat",
+                 "unpack_nhwc_to_nchw", "upsample_nearest", "sampler_step", "set_sm_budget", "gn_stat_slabs", "groupnorm_apply", "linear_lora_ok", "linear_lora", "linear_ln", "linear_stats", "add_noise", "adamw_flat",
                  "mse_partial") + fake_ops.TRAIN_OPS:
         setattr(ops, name, getattr(fake_ops, name))
 
