@@ -30,6 +30,7 @@ _PROTOS = {
     "b200_last_error": (c_char_p, []),
     "b200_debug_timeline": (c_int, [c_void_p, c_int]),
     "b200_set_sm_budget": (c_int, [c_int]),
+    "b200_tmap_cache_hits": (c_long, []),
     "b200_conv_gemm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
@@ -37,6 +38,7 @@ _PROTOS = {
                                       c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                       c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200_gn_stat_slabs": (c_int, [c_int, c_int, c_int]),
+    "b200_gemm_nt": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200_groupnorm_apply": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p]),
     "b200_linear_lora": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
@@ -48,6 +50,7 @@ _PROTOS = {
                                   c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "b200_groupnorm_silu": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
                                     c_int, c_void_p, c_void_p]),
+    "b200_softmax_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_long, c_void_p, c_long, c_float, c_void_p]),
     "b200_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     "b200_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "b200_time_class_embed": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,

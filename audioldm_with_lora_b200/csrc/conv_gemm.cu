@@ -114,6 +114,8 @@ struct ConvGemmParams {
   // any GroupNorm, also one over a concatenation of two tensors.
   float* gn_stat;                   // [NB, gn_slabs, n_valid / 4, 2] or null
   int gn_slabs;                     // slabs per image = tiles_h * (W * BH / 32)
+  int b_dynamic;                    // 1: the "weight" operand is an activation written by the previous kernel in the
+                                    // stream (b200_gemm_nt): its producer warp must wait for that grid like everyone else
 };
 
 // exact-erf GELU to ~2e-7 absolute (Abramowitz-Stegun 7.1.26 erfc; bf16 output rounding is 4e-3 relative):
@@ -228,7 +230,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // weight (B) producer: weights are never written inside a step, so with split producers its TMA stream starts
   // before the previous grid has drained (hides the HBM latency of the first weight tiles; B200_B_EARLY=0 disables).
   pdl_launch_dependents();
-  if (warp != 0 && !(B200_B_EARLY && warp == kProducerBWarp)) pdl_wait();   // warp 0 (A producer): after its index math
+  if (warp != 0 && !(B200_B_EARLY && warp == kProducerBWarp && !p.b_dynamic)) pdl_wait();   // warp 0 (A producer): after its index math
 
   if (warp == 0) {
     // ================================================================ activation (A) TMA producer
@@ -849,13 +851,19 @@ extern "C" int b200_debug_timeline(unsigned long long* host_out, int n) {
   return e == cudaSuccess ? B200_OK : fail(B200_ERR_CUDA, "debug_timeline: %s", cudaGetErrorString(e));
 }
 
+// Hits of the process-wide tensor-map cache (host_util.h) so far: the eager paths re-use encoded descriptors.
+extern "C" long b200_tmap_cache_hits(void) {
+  std::lock_guard<std::mutex> lock(tmap_mutex());
+  return static_cast<long>(tmap_cache_hits());
+}
+
 static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const void* a2, int c2, int nb, int h,
                           int w, int ntaps, int stride, const void* wpacked, int n_pad, int n_valid,
                           const float* bias, const float* rowvec, int rowvec_ld, const void* residual, int res_ld,
                           void* out, int out_ld, int out_fp32, int geglu, int block_n, int max_ctas,
                           int ksplit, float* workspace, int cta_pair, const void* lora_down, int lora_rows, void* t_out,
                           const float* ln_g, const float* ln_ga, const float* ln_ba, float ln_eps, const float* ln_stats,
-                          float* stat_out, void* stream_v, float* gn_stat = nullptr);
+                          float* stat_out, void* stream_v, float* gn_stat = nullptr, int b_dynamic = 0);
 
 // C-ABI: see include/b200ldm.h
 extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, const void* a2, int c2, int nb, int h,
@@ -878,6 +886,18 @@ extern "C" int b200_conv_gemm_gnstat(const void* a0, int c0, const void* a1, int
   return conv_gemm_impl(a0, c0, a1, c1, a2, c2, nb, h, w, ntaps, 1, wpacked, n_pad, n_valid, bias, rowvec, rowvec_ld,
                         residual, res_ld, out, out_ld, 0, 0, block_n, max_ctas, 1, nullptr, cta_pair,
                         nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, nullptr, stream_v, gn_stat);
+}
+
+// out[m, n] = sum_k a[m, k] * b[n, k] (+ residual) with BOTH operands activations (bf16, K-major, written earlier in the
+// stream): the scores S = Q K^T and O = P V of the VAE decoder's head_dim-512 attention.  Same kernel as b200_conv_gemm;
+// the only difference is that the "weight" producer warp honours the programmatic-dependent-launch wait (weights proper
+// are never written inside a step, so b200_conv_gemm lets that warp start before the previous grid has drained).
+// b must be readable for b_rows rows (a multiple of block_n >= n_valid; rows >= n_valid only feed discarded columns).
+extern "C" int b200_gemm_nt(const void* a, int m, int k, const void* b, int b_rows, int n_valid, void* out, int out_ld,
+                            int out_fp32, int block_n, int cta_pair, void* stream_v) {
+  return conv_gemm_impl(a, k, nullptr, 0, nullptr, 0, 1, m, 1, 1, 1, b, b_rows, n_valid, nullptr, nullptr, 0, nullptr, 0, out,
+                        out_ld, out_fp32, 0, block_n, 0, 1, nullptr, cta_pair, nullptr, 0, nullptr, nullptr, nullptr, nullptr,
+                        0.f, nullptr, nullptr, stream_v, nullptr, 1);
 }
 
 // Slabs per image of the statistics b200_conv_gemm_gnstat writes for an [nb, h, w, *] output; 0: this geometry is not
@@ -940,7 +960,7 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
                           void* out, int out_ld, int out_fp32, int geglu, int block_n, int max_ctas,
                           int ksplit, float* workspace, int cta_pair, const void* lora_down, int lora_rows, void* t_out,
                           const float* ln_g, const float* ln_ga, const float* ln_ba, float ln_eps, const float* ln_stats,
-                          float* stat_out, void* stream_v, float* gn_stat) {
+                          float* stat_out, void* stream_v, float* gn_stat, int b_dynamic) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const bool fused_lora = lora_down != nullptr;
   const bool fused_ln = ln_g != nullptr;
@@ -1024,6 +1044,7 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
     p.stat_out = stat_out;
     p.stat_chunks = n_valid / 64;
   }
+  p.b_dynamic = b_dynamic;
   if (gn_stat) {
     B200_CHECK_ARG(p.tma_out && ksplit <= 1 && !geglu && n_valid % 4 == 0 && !fused_ln && !fused_lora && !stat_out,
                    "conv_gemm: gn_stat needs the plain bf16 TMA-store epilogue");

@@ -8,6 +8,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
+
 namespace b200 {
 
 enum { B200_OK = 0, B200_ERR_ARG = -1, B200_ERR_CUDA = -2, B200_ERR_DRIVER = -3, B200_ERR_UNSUPPORTED = -4 };
@@ -50,9 +53,74 @@ inline PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+// Encoded tensor maps are cached by VALUE of their inputs (base pointer, dims, strides, box, swizzle): a descriptor is a
+// pure function of those, so a hit can never be stale.  Under CUDA-graph replay nothing is encoded at all; the cache is
+// for the eager paths (the autograd seam of the fine-tuning step, B200AttnProcessor), where a step re-issues the same
+// ~1000 launches on the same arena addresses and cuTensorMapEncodeTiled (~1.5 us, six per GEMM launch) would dominate
+// the host side.  Process-wide, mutex-protected, bounded (cleared when full).
+struct TmapKey {
+  uint64_t v[12];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < 12; ++i) {
+      h ^= k.v[i];
+      h *= 1099511628211ull;
+    }
+    return static_cast<size_t>(h);
+  }
+};
+inline std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash>& tmap_cache() {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> c;
+  return c;
+}
+inline std::mutex& tmap_mutex() {
+  static std::mutex m;
+  return m;
+}
+inline unsigned long long& tmap_cache_hits() {
+  static unsigned long long n = 0;
+  return n;
+}
+
+inline int make_tmap_bf16_uncached(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                                   const uint64_t* strides_el, const uint32_t* box, CUtensorMapSwizzle swz);
+
 // bf16 tensor, `rank` dims (innermost first), strides in ELEMENTS for dims 1..rank-1.
 inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
                           const uint32_t* box, CUtensorMapSwizzle swz) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.v[0] = reinterpret_cast<uint64_t>(base);
+  key.v[1] = (static_cast<uint64_t>(rank) << 32) | static_cast<uint64_t>(swz);
+  for (int i = 0; i < rank && i < 4; ++i) {
+    key.v[2 + i] = dims[i];
+    key.v[6 + i] = i + 1 < rank ? strides_el[i] : 0;
+  }
+  key.v[10] = (static_cast<uint64_t>(box[0]) << 32) | (rank > 1 ? box[1] : 0);
+  key.v[11] = (static_cast<uint64_t>(rank > 2 ? box[2] : 0) << 32) | (rank > 3 ? box[3] : 0);
+  {
+    std::lock_guard<std::mutex> lock(tmap_mutex());
+    auto it = tmap_cache().find(key);
+    if (it != tmap_cache().end()) {
+      *m = it->second;
+      ++tmap_cache_hits();
+      return B200_OK;
+    }
+  }
+  const int rc = make_tmap_bf16_uncached(m, base, rank, dims, strides_el, box, swz);
+  if (rc == B200_OK) {
+    std::lock_guard<std::mutex> lock(tmap_mutex());
+    if (tmap_cache().size() > 65536) tmap_cache().clear();
+    tmap_cache().emplace(key, *m);
+  }
+  return rc;
+}
+
+inline int make_tmap_bf16_uncached(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                                   const uint64_t* strides_el, const uint32_t* box, CUtensorMapSwizzle swz) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return fail(B200_ERR_DRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint64_t gdim[5], gstr[4];

@@ -318,6 +318,60 @@ groupnorm_apply_kernel(const GnApplyParams p) {
   }
 }
 
+// Row softmax fp32 [rows, ld_s] -> bf16 [rows, ld_p] (columns >= cols written as zero up to cols_pad).  One 256-thread block
+// per row; the row lives in registers between the three passes (max, sum of exp, normalise): cols <= 256 * 32.
+// Used by the VAE decoder's single-head, head_dim-512 mid-block attention (AutoencoderKL.decode, loaded at
+// /root/reference/script/train/train_audioldm_lora.py:370), whose scores S = Q K^T and O = P V run as b200_conv_gemm
+// launches: head_dim 512 does not fit the fused attention kernel's TMEM budget, and the block runs once per clip.
+static constexpr int kSmThreads = 256;
+static constexpr int kSmMaxPer = 32;
+__global__ void __launch_bounds__(kSmThreads)
+softmax_rows_kernel(const float* __restrict__ s, int cols, int cols_pad, size_t ld_s, __nv_bfloat16* __restrict__ pout,
+                    size_t ld_p, float scale_log2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t row = blockIdx.x;
+  const float* src = s + row * ld_s;
+  __nv_bfloat16* dst = pout + row * ld_p;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ float red[kSmThreads / 32];
+  float v[kSmMaxPer];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kSmMaxPer; ++i) {
+    const int c = tid + i * kSmThreads;
+    v[i] = c < cols ? src[c] * scale_log2 : -INFINITY;
+    mx = fmaxf(mx, v[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < kSmThreads / 32; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSmMaxPer; ++i) {
+    v[i] = exp2f(v[i] - mx);          // exp2(-inf) = 0 for the padding
+    sum += v[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < kSmThreads / 32; ++w) sum += red[w];      // fixed order: deterministic
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < kSmMaxPer; ++i) {
+    const int c = tid + i * kSmThreads;
+    if (c < cols_pad) dst[c] = __float2bfloat16(c < cols ? v[i] * inv : 0.f);
+  }
+}
+
 // One warp per row, kLnRows rows per warp in flight (all loads issued before the first reduction: the kernel is bound by
 // bytes in flight per SM, not by arithmetic); C % 8 == 0, C <= 1280.  y = (x - mean) * rstd * gamma + beta  (eps inside sqrt)
 static constexpr int kLnMaxVec = 5;     // 5 * 32 lanes * 8 = 1280 channels
@@ -525,6 +579,18 @@ extern "C" int b200_groupnorm_apply(const void* x0, int c0, const float* st0, in
   if (per_image < 1) per_image = 1;
   B200_CHECK_PDL("groupnorm_apply", launch_pdl(groupnorm_apply_kernel, dim3((unsigned)per_image, nb), dim3(kGnThreads), 0,
                                                stream, 0, p));
+  return B200_OK;
+}
+
+// p[r, c] = softmax_c(scale * s[r, c]) for c < cols, 0 for cols <= c < cols_pad.  s fp32 (row stride ld_s), p bf16 (ld_p).
+extern "C" int b200_softmax_rows(const float* s, int rows, int cols, int cols_pad, long ld_s, void* p, long ld_p, float scale,
+                                 void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(s && p && rows > 0 && cols > 0 && cols_pad >= cols && ld_s >= cols && ld_p >= cols_pad, "softmax_rows: bad args");
+  B200_CHECK_ARG(cols_pad <= kSmThreads * kSmMaxPer, "softmax_rows: at most %d columns", kSmThreads * kSmMaxPer);
+  B200_CHECK_PDL("softmax_rows", launch_pdl(softmax_rows_kernel, dim3(rows), dim3(kSmThreads), 0, stream, 0, s, cols, cols_pad,
+                                            static_cast<size_t>(ld_s), reinterpret_cast<__nv_bfloat16*>(p),
+                                            static_cast<size_t>(ld_p), scale * 1.4426950408889634f));
   return B200_OK;
 }
 

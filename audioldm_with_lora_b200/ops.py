@@ -169,6 +169,21 @@ def conv_gemm(pw: PackedWeight, a0: Tensor, nb: int, h: int, w: int, out: Tensor
 # GroupNorm statistics from the producing conv's epilogue + a one-pass apply kernel.  Parity-tested, but measured on B200
 # it does not pay: the transposed read-back costs the producer ~1.2 us on its critical path, about
 # what the consumer saves.  Opt-in.
+def gemm_nt(a: Tensor, b: Tensor, n_valid: int, out: Tensor, block_n: int, out_ld: Optional[int] = None) -> Tensor:
+    """out[m, :n_valid] = a[m, k] . b[:n_valid, k]^T, both bf16 K-major activations written earlier in the stream (see
+    include/b200ldm.h::b200_gemm_nt).  b: [b_rows, k] with b_rows a multiple of block_n (rows >= n_valid: don't-care)."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous()
+    m, k = a.shape
+    assert b.shape[1] == k and b.shape[0] % block_n == 0 and b.shape[0] >= n_valid and k % 64 == 0 and n_valid % 8 == 0
+    out_fp32 = out.dtype == torch.float32
+    ld = out_ld if out_ld is not None else n_valid
+    info = {"flops": 2.0 * m * n_valid * k, "m": m, "n": n_valid, "k": k, "bn": block_n, "taps": 1, "desc": "nt"} \
+        if _lib.PROFILE is not None else None
+    call("b200_gemm_nt", ptr(a), m, k, ptr(b), b.shape[0], n_valid, ptr(out), ld, int(out_fp32), block_n,
+         int(CTA_PAIR and block_n >= PAIR_MIN_BN), stream(), info=info)
+    return out
+
+
 GN_ONEPASS = os.environ.get("B200_GN_ONEPASS", "0") != "0"
 _SLABS: dict = {}
 
@@ -296,6 +311,14 @@ def groupnorm_silu(x0: Tensor, c0: int, x1: Optional[Tensor], c1: int, nb: int, 
     call("b200_groupnorm_silu", ptr(x0), c0, ptr(x1) if c1 else None, c1, nb, hw, groups, ptr(gamma), ptr(beta),
          float(eps), int(silu), ptr(y), stream(), info=info)
     return y
+
+
+def softmax_rows(s: Tensor, rows: int, cols: int, cols_pad: int, p: Tensor, scale: float = 1.0) -> Tensor:
+    """p[r, :cols] = softmax(scale * s[r, :cols]), zero up to cols_pad; s fp32 [rows, ld_s], p bf16 [rows, ld_p]."""
+    assert s.dtype == torch.float32 and p.dtype == torch.bfloat16 and s.dim() == 2 and p.dim() == 2
+    assert s.stride(1) == 1 and p.stride(1) == 1 and s.shape[0] >= rows and p.shape[0] >= rows
+    call("b200_softmax_rows", ptr(s), rows, cols, cols_pad, s.stride(0), ptr(p), p.stride(0), float(scale), stream())
+    return p
 
 
 def layernorm(x: Tensor, m: int, c: int, gamma: Tensor, beta: Tensor, eps: float, y: Tensor) -> Tensor:

@@ -87,7 +87,7 @@ class _LoopState:
 class AudioLDMPipeline:
     def __init__(self, unet: UNet2DConditionModel, scheduler: Optional[DDIMScheduler] = None, vae=None, vocoder=None,
                  text_encoder=None, tokenizer=None, tail_dtype: torch.dtype = torch.bfloat16, use_cuda_graph: bool = True,
-                 branches: Optional[int] = None):
+                 branches: Optional[int] = None, b200_vae: Optional[bool] = None):
         self.unet = unet
         self.scheduler = scheduler or DDIMScheduler()
         self.vae, self.vocoder = vae, vocoder
@@ -101,6 +101,14 @@ class AudioLDMPipeline:
         self.branches = int(os.environ.get("B200_BRANCHES", "1")) if branches is None else int(branches)
         self._loops: Dict[tuple, _LoopState] = {}
         self._tail_graphs: Dict[tuple, Optional[tuple]] = {}
+        # VAE decoder: a torch module with diffusers key names is re-hosted on the sm_100a kernels (vae.B200VaeDecoder,
+        # SURVEY 8(f) item 1) unless b200_vae=False / B200_VAE=0 keeps it on the torch-eager reference path.
+        if b200_vae is None:
+            b200_vae = os.environ.get("B200_VAE", "1") != "0"
+        if (self.vae is not None and b200_vae and self.device.type == "cuda" and isinstance(self.vae, torch.nn.Module)
+                and any(k.startswith("decoder.mid_block") for k in self.vae.state_dict())):
+            from .vae import from_torch_decoder
+            self.vae = from_torch_decoder(self.vae, self.device)
         if self.vae is not None:
             self.vae = self.vae.to(self.device, tail_dtype).eval()
         if self.vocoder is not None:

@@ -31,6 +31,10 @@ const char* b200_last_error(void);
  * points (kernel entry, after the prologue, first operands landed, last MMA committed, epilogue done, exit);
  * this copies the first n (<= 32) records of the most recent launch to host memory. */
 int b200_debug_timeline(unsigned long long* host_out, int n);
+/* TMA descriptors (CUtensorMap) are cached process-wide by the value of their inputs (pointer, shape, strides, box), so
+ * eager callers that re-issue the same launches on the same buffers -- the autograd seam of the fine-tuning step, the
+ * attention-processor seam -- do not re-encode six descriptors per GEMM launch.  Returns the number of cache hits so far. */
+long b200_tmap_cache_hits(void);
 
 /* Implicit-GEMM convolution / linear layer on tcgen05 tensor cores (TMA-fed, TMEM accumulator).
  *   out[pix, n] = epi( sum_seg sum_tap sum_c A_seg[pix @ tap, c] * wpacked[n, k(seg,tap,c)] )
@@ -66,6 +70,13 @@ int b200_conv_gemm_gnstat(const void* a0, int c0, const void* a1, int c1, const 
                           int rowvec_ld, const void* residual, int res_ld, void* out, int out_ld, int block_n,
                           int max_ctas, int cta_pair, float* gn_stat, void* stream);
 int b200_gn_stat_slabs(int nb, int h, int w);
+
+/* out[m, n] = sum_k a[m, k] * b[n, k] with BOTH operands bf16 K-major activations produced earlier in the stream (b200_conv_gemm's
+ * kernel with the weight-operand producer made to wait for the previous grid): S = Q K^T and O = P V of the VAE decoder's
+ * single-head, head_dim-512 attention (AutoencoderKL.decode, train_audioldm_lora.py:370 / app.py:14).  b must be readable for
+ * b_rows rows (multiple of block_n, >= n_valid); out bf16 or fp32, leading dim out_ld. */
+int b200_gemm_nt(const void* a, int m, int k, const void* b, int b_rows, int n_valid, void* out, int out_ld, int out_fp32,
+                 int block_n, int cta_pair, void* stream);
 
 /* Linear layer with the rank-r LoRA branch computed inside the kernel (peft lora.Linear, unmerged; LoRA config at
  * generate_audio.py:21-29, train_audioldm_lora.py:378-385):  out = x W^T + (x A^T)(s B)^T (+ bias + residual).
@@ -116,6 +127,13 @@ int b200_groupnorm_silu(const void* x0, int c0, const void* x1, int c1, int nb, 
 int b200_groupnorm_apply(const void* x0, int c0, const float* st0, int slabs0, const void* x1, int c1, const float* st1,
                          int slabs1, int nb, int hw, int groups, const float* gamma, const float* beta, float eps,
                          int silu, void* y, void* stream);
+
+/* Row softmax p[r, :cols] = softmax(scale * s[r, :cols]) (fp32 in, bf16 out, columns cols..cols_pad-1 zeroed so that p
+ * can be the K-padded A operand of the following P.V GEMM).  With two b200_conv_gemm launches (S = Q K^T, O = P V) this is
+ * the single-head, head_dim-512 attention of the VAE decoder's mid block (AutoencoderKL.decode inside
+ * AudioLDMPipeline.__call__: /root/reference/app.py:14; VAE loaded at train_audioldm_lora.py:370). */
+int b200_softmax_rows(const float* s, int rows, int cols, int cols_pad, long ld_s, void* p, long ld_p, float scale,
+                      void* stream);
 
 /* LayerNorm over the last dim of a [m, c] bf16 matrix.  Replaces F.layer_norm in
  * BasicTransformerBlock.norm1/2/3 (diffusers, via train_audioldm_lora.py:539-546). */
