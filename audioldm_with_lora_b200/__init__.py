@@ -12,11 +12,12 @@ from .model import (Attention, B200AttnProcessor, LoraLinear, UNet2DConditionMod
 from .pipeline import AudioLDMPipeline, AudioPipelineOutput
 from .scheduler import DDIMScheduler, PNDMScheduler
 from .vae import B200VaeDecoder
+from .vocoder import B200HifiGan
 
 __all__ = [
     "AUDIOLDM_L", "AUDIOLDM_S", "CONFIGS", "UNetConfig", "LoraConfig", "convert_state_dict_to_diffusers",
     "parse_lora_state_dict", "to_peft_state_dict", "save_lora_checkpoint", "load_lora_checkpoint",
     "merge_lora_into_state_dict", "Attention", "B200AttnProcessor", "LoraLinear",
     "UNet2DConditionModel", "UNet2DConditionOutput", "get_peft_model", "get_peft_model_state_dict",
-    "AudioLDMPipeline", "AudioPipelineOutput", "DDIMScheduler", "PNDMScheduler", "B200VaeDecoder",
+    "AudioLDMPipeline", "AudioPipelineOutput", "DDIMScheduler", "PNDMScheduler", "B200VaeDecoder", "B200HifiGan",
 ]

@@ -114,6 +114,16 @@ struct ConvGemmParams {
   // any GroupNorm, also one over a concatenation of two tensors.
   float* gn_stat;                   // [NB, gn_slabs, n_valid / 4, 2] or null
   int gn_slabs;                     // slabs per image = tiles_h * (W * BH / 32)
+  // Tap walk of segment 0: tap t reads the input at (dh, dw) = (dh0 + (t / tw) * dh_step, dw0 + t % tw), tw = dw_end - dw0.
+  // 3x3 conv: dh0 = dw0 = -1, dw_end = 2, dh_step = 1.  1-D conv over [nb, L, C] (W = 1; b200_conv1d): dw0 = 0, dw_end = 1,
+  // dh0 = -(k - 1) / 2 * dilation, dh_step = dilation; one phase of a transposed 1-D conv: dh0 = b, dh_step = -1.
+  int dh0, dw0, dw_end, dh_step;
+  // kAct (b200_conv1d): out = act(acc + bias + unact(residual)).  act: LeakyReLU max(v, act_slope v) (slope 1 = identity) or,
+  // act_tanh, tanh(v).  The residual tensor may itself be stored POST-activation (y = lrelu(x, s)): x = min(y, y / s) is
+  // recovered on the fly with res_neg_gain = 1 / s (1 = the residual is stored as it is).
+  float act_slope;
+  float res_neg_gain;
+  int act_tanh;
   int b_dynamic;                    // 1: the "weight" operand is an activation written by the previous kernel in the
                                     // stream (b200_gemm_nt): its producer warp must wait for that grid like everyone else
 };
@@ -164,7 +174,27 @@ __device__ __forceinline__ void ln_affine8(float (&v)[8], const float* g, const 
   v[6] = fmaf(v[6] - mu * g1.z, rs, b1.z); v[7] = fmaf(v[7] - mu * g1.w, rs, b1.w);
 }
 
-template <bool kCta2, bool kLora = false, bool kLn = false, bool kStat = false, bool kGn = false>
+// b200_conv1d epilogue pieces (HiFi-GAN): residual stored post-LeakyReLU -> pre-activation value, and the output activation
+__device__ __forceinline__ void add_res8_unact(float (&v)[8], const uint4 rr, float neg_gain) {
+  const float r[8] = {bf16_lo(rr.x), bf16_hi(rr.x), bf16_lo(rr.y), bf16_hi(rr.y),
+                      bf16_lo(rr.z), bf16_hi(rr.z), bf16_lo(rr.w), bf16_hi(rr.w)};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] += fminf(r[j], r[j] * neg_gain);      // neg_gain >= 1: only negative values are scaled
+}
+__device__ __forceinline__ void act8(float (&v)[8], float slope, int use_tanh) {
+  if (use_tanh) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float e = __expf(2.0f * fminf(fmaxf(v[j], -15.f), 15.f));     // tanh(x) = 1 - 2 / (e^{2x} + 1)
+      v[j] = 1.0f - __fdividef(2.0f, e + 1.0f);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], v[j] * slope);        // slope <= 1
+  }
+}
+
+template <bool kCta2, bool kLora = false, bool kLn = false, bool kStat = false, bool kGn = false, bool kAct = false>
 __global__ void __launch_bounds__(B200_GEMM_LB_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
@@ -272,12 +302,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int h0 = (m_tile - n_img * p.tiles_h) * p.BH;
         const int n0 = n_img * p.BNI;
         int kb = kb_begin;
-        int cb = 0, dh = 0, dw = 0;
-        if (p.ntaps == 9) { dh = -1; dw = -1; }
+        int cb = 0, dh = p.dh0, dw = p.dw0;
+        const int dw0 = p.dw0, dw_end = p.dw_end, dh_step = p.dh_step;
         if (kb > 0 && kb < seg_end0) {
           const int tap = kb / cb0;
           cb = kb - tap * cb0;
-          if (p.ntaps == 9) { dh = tap / 3 - 1; dw = tap - (tap / 3) * 3 - 1; }
+          const int tw = dw_end - dw0;
+          dh += (tap / tw) * dh_step;
+          dw += tap % tw;
         }
         // PDL: the activations are the previous kernel's output (the index math above overlapped its tail)
         if (t == tile0) { pdl_wait(); TL(2); }
@@ -307,10 +339,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
             PKB(64, kb - kb_begin);
             c += kBlockK;
-            if (--left == 0) {              // next tap: (dh, dw) walk the 3x3 window row by row
+            if (--left == 0) {              // next tap: (dh, dw) walk the window row by row
               left = cb0;
               c = 0;
-              if (++dw == 2) { dw = -1; ++hh; }
+              if (++dw == dw_end) { dw = dw0; hh += dh_step; }
             }
           }
         }
@@ -632,10 +664,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                   if (p.rowvec) add8(v, p.rowvec + static_cast<size_t>(n) * p.rowvec_ld + cg);
                   if (p.residual) {
                     const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + pix * p.res_ld + cg);
-                    v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
-                    v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                    if (kAct) add_res8_unact(v, rr, p.res_neg_gain);
+                    else {
+                      v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                      v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                    }
                   }
                 }
+                if (kAct) act8(v, p.act_slope, p.act_tanh);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) pk[hh * 16 + g * 4 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
               }
@@ -749,9 +785,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 if (p.rowvec) add8(v, p.rowvec + static_cast<size_t>(n) * p.rowvec_ld + cg);
                 if (p.residual) {
                   const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + pix * p.res_ld + cg);
-                  v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
-                  v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                  if (kAct) add_res8_unact(v, rr, p.res_neg_gain);
+                  else {
+                    v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                    v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                  }
                 }
+                if (kAct) act8(v, p.act_slope, p.act_tanh);
                 if (p.out_fp32) {
                   float* o = reinterpret_cast<float*>(p.out) + split * p.split_stride + pix * p.out_ld + cg;
                   *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
@@ -863,7 +903,18 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
                           void* out, int out_ld, int out_fp32, int geglu, int block_n, int max_ctas,
                           int ksplit, float* workspace, int cta_pair, const void* lora_down, int lora_rows, void* t_out,
                           const float* ln_g, const float* ln_ga, const float* ln_ba, float ln_eps, const float* ln_stats,
-                          float* stat_out, void* stream_v, float* gn_stat = nullptr, int b_dynamic = 0);
+                          float* stat_out, void* stream_v, float* gn_stat = nullptr, int b_dynamic = 0,
+                          const struct Conv1dOpts* c1d = nullptr);
+
+// 1-D tap walk and output geometry of b200_conv1d (everything else is the 2-D kernel with W = 1)
+struct Conv1dOpts {
+  int dh0, dh_step;        // first tap's row offset and the step between taps
+  int m_h;                 // output rows per image (>= or <= the input length h: transposed-conv phases)
+  long out_batch_stride;   // elements between images of the output (0: m_h * out_ld)
+  float act_slope;         // LeakyReLU slope applied after bias / residual (1: identity)
+  float res_neg_gain;      // residual stored post-LeakyReLU(s): 1 / s; plain residual: 1
+  int act_tanh;            // tanh instead of LeakyReLU
+};
 
 // C-ABI: see include/b200ldm.h
 extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, const void* a2, int c2, int nb, int h,
@@ -898,6 +949,25 @@ extern "C" int b200_gemm_nt(const void* a, int m, int k, const void* b, int b_ro
   return conv_gemm_impl(a, k, nullptr, 0, nullptr, 0, 1, m, 1, 1, 1, b, b_rows, n_valid, nullptr, nullptr, 0, nullptr, 0, out,
                         out_ld, out_fp32, 0, block_n, 0, 1, nullptr, cta_pair, nullptr, 0, nullptr, nullptr, nullptr, nullptr,
                         0.f, nullptr, nullptr, stream_v, nullptr, 1);
+}
+
+// 1-D convolution over time-major bf16 activations x [nb, len, c]  (HiFi-GAN: Conv1d with dilation, and -- one launch per
+// output phase -- ConvTranspose1d); see include/b200ldm.h::b200_conv1d:
+//   out[n, q, :] = act( bias + sum_{t < ntaps} x[n, q + dh0 + t * dh_step, :] . W_t^T  + unact(residual[n, q, :]) ),   q < m_rows
+// rows outside [0, len) read as zero (TMA fill = the convolution's zero padding).  wpacked bf16 [n_pad, ntaps * c], tap-major.
+extern "C" int b200_conv1d(const void* x, int c, int nb, int len, int ntaps, int dh0, int dh_step, int m_rows,
+                           const void* wpacked, int n_pad, int n_valid, const float* bias, const void* residual, int res_ld,
+                           float res_neg_gain, void* out, int out_ld, long out_batch_stride, int out_fp32, float act_slope,
+                           int act_tanh, int block_n, int cta_pair, void* stream_v) {
+  Conv1dOpts o;
+  o.dh0 = dh0; o.dh_step = dh_step; o.m_h = m_rows; o.out_batch_stride = out_batch_stride;
+  o.act_slope = act_slope; o.res_neg_gain = res_neg_gain; o.act_tanh = act_tanh;
+  B200_CHECK_ARG(!residual || m_rows == len, "conv1d: a residual needs m_rows == len");
+  B200_CHECK_ARG(!out_fp32 || out_batch_stride == 0, "conv1d: fp32 output is contiguous");
+  B200_CHECK_ARG(act_slope <= 1.0f && act_slope >= 0.f && res_neg_gain >= 1.0f, "conv1d: needs 0 <= act_slope <= 1 <= res_neg_gain");
+  return conv_gemm_impl(x, c, nullptr, 0, nullptr, 0, nb, len, 1, ntaps, 1, wpacked, n_pad, n_valid, bias, nullptr, 0, residual,
+                        res_ld, out, out_ld, out_fp32, 0, block_n, 0, 1, nullptr, cta_pair, nullptr, 0, nullptr, nullptr, nullptr,
+                        nullptr, 0.f, nullptr, nullptr, stream_v, nullptr, 0, &o);
 }
 
 // Slabs per image of the statistics b200_conv_gemm_gnstat writes for an [nb, h, w, *] output; 0: this geometry is not
@@ -960,8 +1030,9 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
                           void* out, int out_ld, int out_fp32, int geglu, int block_n, int max_ctas,
                           int ksplit, float* workspace, int cta_pair, const void* lora_down, int lora_rows, void* t_out,
                           const float* ln_g, const float* ln_ga, const float* ln_ba, float ln_eps, const float* ln_stats,
-                          float* stat_out, void* stream_v, float* gn_stat, int b_dynamic) {
+                          float* stat_out, void* stream_v, float* gn_stat, int b_dynamic, const Conv1dOpts* c1d) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int m_h = c1d ? c1d->m_h : h;               // output rows per image
   const bool fused_lora = lora_down != nullptr;
   const bool fused_ln = ln_g != nullptr;
   if (fused_ln) {
@@ -978,7 +1049,9 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
   }
   B200_CHECK_ARG(stride == 1 || (stride == 2 && ntaps == 9 && !residual), "conv_gemm: stride %d unsupported", stride);
   B200_CHECK_ARG(a0 && wpacked && out, "conv_gemm: null pointer");
-  B200_CHECK_ARG(ntaps == 1 || ntaps == 9, "conv_gemm: ntaps must be 1 or 9 (got %d)", ntaps);
+  B200_CHECK_ARG(ntaps == 1 || ntaps == 9 || (c1d && ntaps >= 1 && ntaps <= 16), "conv_gemm: ntaps must be 1 or 9 (got %d)", ntaps);
+  B200_CHECK_ARG(!c1d || (w == 1 && stride == 1 && ksplit <= 1 && !geglu && !fused_lora && !fused_ln && !stat_out && !gn_stat &&
+                          c1 == 0 && c2 == 0 && m_h > 0), "conv1d: needs a plain [nb, L, C] layer");
   B200_CHECK_ARG(c0 > 0 && c0 % 64 == 0 && c1 % 64 == 0 && c2 % 64 == 0, "conv_gemm: channels must be multiples of 64 (%d,%d,%d)", c0, c1, c2);
   B200_CHECK_ARG(((c1 == 0) == (a1 == nullptr) || fused_lora) && (c2 == 0) == (a2 == nullptr), "conv_gemm: segment pointer/channel mismatch");
   B200_CHECK_ARG(block_n >= 32 && block_n <= 256 && block_n % 32 == 0, "conv_gemm: block_n %d unsupported", block_n);
@@ -993,17 +1066,25 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
 
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
-  if (pick_box(h, w, nb, &p.BH, &p.BNI) != 0) return fail(B200_ERR_UNSUPPORTED, "conv_gemm: width %d does not divide 128", w);
+  if (pick_box(m_h, w, nb, &p.BH, &p.BNI) != 0) return fail(B200_ERR_UNSUPPORTED, "conv_gemm: width %d does not divide 128", w);
+  if (c1d) {
+    p.dh0 = c1d->dh0; p.dh_step = c1d->dh_step; p.dw0 = 0; p.dw_end = 1;
+    p.act_slope = c1d->act_slope; p.res_neg_gain = c1d->res_neg_gain; p.act_tanh = c1d->act_tanh;
+  } else if (ntaps == 9) {
+    p.dh0 = -1; p.dw0 = -1; p.dw_end = 2; p.dh_step = 1;
+  } else {
+    p.dh0 = 0; p.dw0 = 0; p.dw_end = 1; p.dh_step = 0;
+  }
   p.cb0 = c0 / 64;
   p.ntaps = ntaps;
   p.seg_end0 = ntaps * p.cb0;
   p.seg_end1 = p.seg_end0 + c1 / 64;
   p.num_kb = p.seg_end1 + c2 / 64;
-  p.H = h; p.W = w; p.NB = nb;
+  p.H = m_h; p.W = w; p.NB = nb;          // the epilogue's geometry (== the input's except for b200_conv1d with m_h != h)
   p.stride = stride;
   p.Hout = stride == 2 ? (h - 1) / 2 + 1 : h;
   p.Wout = stride == 2 ? (w - 1) / 2 + 1 : w;
-  p.tiles_h = (h + p.BH - 1) / p.BH;
+  p.tiles_h = (m_h + p.BH - 1) / p.BH;
   p.num_m_tiles = p.tiles_h * ((nb + p.BNI - 1) / p.BNI);
   p.num_n_tiles = n_pad / block_n;
   p.block_n = block_n;
@@ -1014,7 +1095,7 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
   p.tma_out = (!out_fp32 && stride == 1 && block_n % 64 == 0) ? 1 : 0;
   p.ksplit = 1;
   p.kb_per_split = p.num_kb;
-  const size_t m_total = static_cast<size_t>(nb) * h * w;
+  const size_t m_total = static_cast<size_t>(nb) * m_h * w;
   if (ksplit > 1) {
     p.kb_per_split = (p.num_kb + ksplit - 1) / ksplit;
     p.ksplit = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;      // no empty splits
@@ -1119,8 +1200,8 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
     if (bh > p.BH) bh = p.BH;
     const int bn = 32 / (bw * bh);
     const uint64_t L = out_ld;
-    uint64_t dims[4] = {(uint64_t)n_valid, (uint64_t)w, (uint64_t)h, (uint64_t)nb};
-    uint64_t strides[3] = {L, L * w, L * w * h};
+    uint64_t dims[4] = {(uint64_t)n_valid, (uint64_t)w, (uint64_t)m_h, (uint64_t)nb};
+    uint64_t strides[3] = {L, L * w, (c1d && c1d->out_batch_stride) ? (uint64_t)c1d->out_batch_stride : L * w * m_h};
     uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
     int rc = make_tmap_bf16(&tO, out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -1142,13 +1223,18 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
     cudaFuncSetAttribute(conv_gemm_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     cudaFuncSetAttribute(conv_gemm_kernel<false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     cudaFuncSetAttribute(conv_gemm_kernel<true, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaFuncSetAttribute(conv_gemm_kernel<false, false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaFuncSetAttribute(conv_gemm_kernel<true, false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   }
   int grid = p.num_m_groups * p.num_n_tiles * p.ksplit;
   int cap = max_ctas > 0 ? max_ctas : num_sms;
   if (cta2) {
     if (grid > cap / 2) grid = cap / 2;
     if (grid < 1) grid = 1;
-    if (gn_stat)
+    if (c1d)
+      B200_CHECK_PDL("conv1d(2-CTA)", launch_pdl(conv_gemm_kernel<true, false, false, false, false, true>, dim3(2 * grid),
+                                                 dim3(kThreads), (size_t)smem_bytes, stream, 2, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+    else if (gn_stat)
       B200_CHECK_PDL("conv_gemm_gnstat(2-CTA)", launch_pdl(conv_gemm_kernel<true, false, false, false, true>, dim3(2 * grid),
                                                            dim3(kThreads), (size_t)smem_bytes, stream, 2, tA[0], tA[1], tA[2], tB,
                                                            tO, tLA, p));
@@ -1157,7 +1243,10 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
                                                     stream, 2, tA[0], tA[1], tA[2], tB, tO, tLA, p));
   } else {
     if (grid > cap) grid = cap;
-    if (gn_stat)
+    if (c1d)
+      B200_CHECK_PDL("conv1d", launch_pdl(conv_gemm_kernel<false, false, false, false, false, true>, dim3(grid), dim3(kThreads),
+                                               (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+    else if (gn_stat)
       B200_CHECK_PDL("conv_gemm_gnstat", launch_pdl(conv_gemm_kernel<false, false, false, false, true>, dim3(grid), dim3(kThreads),
                                                     (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
     else if (stat_out && !fused_ln && fused_lora)

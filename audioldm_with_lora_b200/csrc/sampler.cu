@@ -228,6 +228,44 @@ __global__ void upsample_nearest_kernel(const uint4* __restrict__ x, int nb, int
   }
 }
 
+// HiFi-GAN: mean of the three residual blocks of an upsampling stage + the LeakyReLU in front of the next layer.  The
+// block outputs are stored post-LeakyReLU(in_slope) (b200_conv1d's convention): x = min(a, a / in_slope).
+__global__ void lrelu_mean3_kernel(const uint4* __restrict__ a0, const uint4* __restrict__ a1, const uint4* __restrict__ a2,
+                                   size_t nvec, float in_neg_gain, float out_slope, uint4* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 u0 = a0[i], u1 = a1[i], u2 = a2[i];
+    const uint32_t w0[4] = {u0.x, u0.y, u0.z, u0.w}, w1[4] = {u1.x, u1.y, u1.z, u1.w}, w2[4] = {u2.x, u2.y, u2.z, u2.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float r[2];
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        const float x0 = hlf ? bf16_hi(w0[j]) : bf16_lo(w0[j]);
+        const float x1 = hlf ? bf16_hi(w1[j]) : bf16_lo(w1[j]);
+        const float x2 = hlf ? bf16_hi(w2[j]) : bf16_lo(w2[j]);
+        const float m = (fminf(x0, x0 * in_neg_gain) + fminf(x1, x1 * in_neg_gain) + fminf(x2, x2 * in_neg_gain)) * (1.0f / 3.0f);
+        r[hlf] = fmaxf(m, m * out_slope);
+      }
+      o[j] = pack_bf16x2(r[0], r[1]);
+    }
+    y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float4* __restrict__ x, size_t nvec, uint2* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = x[i];
+    y[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
 // ---------------------------------------------------------------------------------- fine-tuning tail
 __global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                                  const float* __restrict__ sa, const float* __restrict__ sb, int nb, size_t per,
@@ -368,6 +406,28 @@ extern "C" int b200_upsample_nearest(const void* x, int nb, int h, int w, int c,
   B200_CHECK_PDL("upsample_nearest", launch_pdl(upsample_nearest_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, 0,
                                                 reinterpret_cast<const uint4*>(x), nb, h, w, c / 8, ho, wo,
                                                 reinterpret_cast<uint4*>(y)));
+  return B200_OK;
+}
+
+extern "C" int b200_lrelu_mean3(const void* a0, const void* a1, const void* a2, long n, float in_slope, float out_slope,
+                                void* y, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(a0 && a1 && a2 && y && n > 0 && n % 8 == 0 && in_slope > 0.f && in_slope <= 1.f && out_slope >= 0.f &&
+                 out_slope <= 1.f, "lrelu_mean3: bad args");
+  const size_t nvec = static_cast<size_t>(n) / 8;
+  B200_CHECK_PDL("lrelu_mean3", launch_pdl(lrelu_mean3_kernel, dim3(grid_for(nvec, 256)), dim3(256), 0, stream, 0,
+                                           reinterpret_cast<const uint4*>(a0), reinterpret_cast<const uint4*>(a1),
+                                           reinterpret_cast<const uint4*>(a2), nvec, 1.0f / in_slope, out_slope,
+                                           reinterpret_cast<uint4*>(y)));
+  return B200_OK;
+}
+
+extern "C" int b200_f32_to_bf16(const float* x, long n, void* y, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(x && y && n > 0 && n % 4 == 0, "f32_to_bf16: bad args");
+  const size_t nvec = static_cast<size_t>(n) / 4;
+  B200_CHECK_PDL("f32_to_bf16", launch_pdl(f32_to_bf16_kernel, dim3(grid_for(nvec, 256)), dim3(256), 0, stream, 0,
+                                           reinterpret_cast<const float4*>(x), nvec, reinterpret_cast<uint2*>(y)));
   return B200_OK;
 }
 

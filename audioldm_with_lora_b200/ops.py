@@ -513,3 +513,46 @@ def mse_grad(pred_nhwc: Tensor, noise_nchw: Tensor, nb: int, hw: int, c_pad: int
 def lora_refresh(descs_dev: Tensor, n: int, flat: Tensor) -> None:
     assert descs_dev.dtype == torch.uint8 and flat.dtype == torch.float32
     call("b200_lora_refresh", ptr(descs_dev), n, ptr(flat), stream())
+
+
+# ------------------------------------------------------------------------------------------ HiFi-GAN vocoder
+def conv1d(pw: PackedWeight, x: Tensor, nb: int, length: int, out: Tensor, *, dh0: int, dh_step: int,
+           m_rows: Optional[int] = None, residual: Optional[Tensor] = None, res_slope: float = 1.0, act_slope: float = 1.0,
+           act_tanh: bool = False, out_ld: Optional[int] = None, out_batch_stride: int = 0,
+           cta_pair: Optional[bool] = None) -> Tensor:
+    """One Conv1d (or one output phase of a ConvTranspose1d) over time-major x [nb, length, c]; see
+    include/b200ldm.h::b200_conv1d.  residual is stored post-LeakyReLU(res_slope) (1.0: plain)."""
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() == nb * length * pw.c0 and pw.c1 == 0 and pw.c2 == 0
+    rows = length if m_rows is None else m_rows
+    out_fp32 = out.dtype == torch.float32
+    assert out_fp32 or out.dtype == torch.bfloat16
+    ld = out_ld if out_ld is not None else pw.n_valid
+    res_ld = 0
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.numel() == nb * length * pw.n_valid
+        res_ld = pw.n_valid
+    info = None
+    if _lib.PROFILE is not None:
+        info = {"flops": 2.0 * nb * rows * pw.macs_per_row, "m": nb * rows, "n": pw.n_valid, "k": pw.k, "bn": pw.block_n,
+                "taps": pw.ntaps, "desc": "conv1d"}
+    pair = (int(CTA_PAIR and pw.block_n >= PAIR_MIN_BN) if cta_pair is None else (2 if cta_pair else 0))
+    call("b200_conv1d", ptr(x), pw.c0, nb, length, pw.ntaps, dh0, dh_step, rows, ptr(pw.w), pw.n_pad, pw.n_valid, ptr(pw.bias),
+         ptr(residual), res_ld, 1.0 / res_slope, ptr(out), ld, out_batch_stride, int(out_fp32), float(act_slope),
+         int(act_tanh), pw.block_n, pair, stream(), info=info)
+    return out
+
+
+def lrelu_mean3(a0: Tensor, a1: Tensor, a2: Tensor, in_slope: float, out_slope: float, y: Tensor) -> Tensor:
+    """y = leaky_relu((x0 + x1 + x2) / 3, out_slope) with a_i = leaky_relu(x_i, in_slope) stored; see b200_lrelu_mean3."""
+    for t in (a0, a1, a2, y):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.numel() == y.numel()
+    info = {"desc": f"n{y.numel()}", "bytes": 8.0 * y.numel()} if _lib.PROFILE is not None else None
+    call("b200_lrelu_mean3", ptr(a0), ptr(a1), ptr(a2), y.numel(), float(in_slope), float(out_slope), ptr(y), stream(), info=info)
+    return y
+
+
+def f32_to_bf16(x: Tensor, y: Tensor) -> Tensor:
+    assert x.dtype == torch.float32 and y.dtype == torch.bfloat16 and x.is_contiguous() and y.is_contiguous()
+    assert x.numel() == y.numel()
+    call("b200_f32_to_bf16", ptr(x), x.numel(), ptr(y), stream())
+    return y

@@ -8,7 +8,8 @@ drives it: /root/reference/app.py:14 (`pipe(prompt, num_inference_steps=200, aud
 The denoising loop -- CFG-duplicated UNet forward, guidance combine, scheduler update -- is ONE
 CUDA graph per (batch, length) replayed `num_inference_steps` times: the timestep, the update
 coefficients and the next UNet input all live on the device (csrc/sampler.cu), so the loop has no
-host synchronisation.  VAE decode and the HiFi-GAN vocoder stay torch-eager (BASELINE.json north_star).
+host synchronisation.  The tail (VAE decode, HiFi-GAN vocoder) runs on the same kernels by default (vae.py, vocoder.py);
+b200_vae=False / b200_vocoder=False keep the torch-eager reference path BASELINE.json's north_star describes.
 """
 from __future__ import annotations
 
@@ -87,7 +88,7 @@ class _LoopState:
 class AudioLDMPipeline:
     def __init__(self, unet: UNet2DConditionModel, scheduler: Optional[DDIMScheduler] = None, vae=None, vocoder=None,
                  text_encoder=None, tokenizer=None, tail_dtype: torch.dtype = torch.bfloat16, use_cuda_graph: bool = True,
-                 branches: Optional[int] = None, b200_vae: Optional[bool] = None):
+                 branches: Optional[int] = None, b200_vae: Optional[bool] = None, b200_vocoder: Optional[bool] = None):
         self.unet = unet
         self.scheduler = scheduler or DDIMScheduler()
         self.vae, self.vocoder = vae, vocoder
@@ -111,6 +112,15 @@ class AudioLDMPipeline:
             self.vae = from_torch_decoder(self.vae, self.device)
         if self.vae is not None:
             self.vae = self.vae.to(self.device, tail_dtype).eval()
+        # HiFi-GAN vocoder: transformers' SpeechT5HifiGan is re-hosted the same way (vocoder.B200HifiGan)
+        # unless b200_vocoder=False / B200_VOCODER=0.
+        if b200_vocoder is None:
+            b200_vocoder = os.environ.get("B200_VOCODER", "1") != "0"
+        if (self.vocoder is not None and b200_vocoder and self.device.type == "cuda" and isinstance(self.vocoder, torch.nn.Module)
+                and type(self.vocoder).__name__ == "SpeechT5HifiGan" and not getattr(self.vocoder.config, "normalize_before", False)
+                and len(self.vocoder.config.resblock_kernel_sizes) == 3):
+            from .vocoder import from_torch_vocoder
+            self.vocoder = from_torch_vocoder(self.vocoder, self.device)
         if self.vocoder is not None:
             self.vocoder = self.vocoder.to(self.device, tail_dtype).eval()
         nblocks = len(self.vae.config.block_out_channels) if self.vae is not None else 3

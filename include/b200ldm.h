@@ -78,6 +78,34 @@ int b200_gn_stat_slabs(int nb, int h, int w);
 int b200_gemm_nt(const void* a, int m, int k, const void* b, int b_rows, int n_valid, void* out, int out_ld, int out_fp32,
                  int block_n, int cta_pair, void* stream);
 
+/* 1-D convolution over time-major bf16 activations x [nb, len, c] -- the layers of the HiFi-GAN vocoder
+ * (transformers SpeechT5HifiGan, loaded at train_audioldm_lora.py:371 and run at the end of AudioLDMPipeline.__call__:
+ * /root/reference/app.py:14, generate_audio.py:47-52): nn.Conv1d with dilation, and -- one launch per output phase --
+ * nn.ConvTranspose1d.  Same tcgen05 implicit-GEMM kernel as b200_conv_gemm with a 1-D tap walk:
+ *   out[n, q, :] = act( bias + sum_{t < ntaps} x[n, q + dh0 + t * dh_step, :] . W_t^T + unact(residual[n, q, :]) ),  q < m_rows
+ * rows outside [0, len) read as zero (the TMA fill is the convolution's zero padding).  wpacked bf16 [n_pad, ntaps * c],
+ * tap-major; c a multiple of 64.
+ *   Conv1d(k, dilation d, padding d (k - 1) / 2): dh0 = -d (k - 1) / 2, dh_step = d, m_rows = len, taps W[:, :, t].
+ *   Phase phi of ConvTranspose1d(k, stride s, padding p): a = (phi + p) % s, b = (phi + p) / s, taps W[:, :, s t + a]^T,
+ *   dh0 = b, dh_step = -1, m_rows = ceil((len_out - phi) / s), out = y + phi * c_out, out_ld = s * c_out,
+ *   out_batch_stride = len_out * c_out (0: m_rows * out_ld).
+ * act: LeakyReLU with slope act_slope in [0, 1] (1 = identity) or, act_tanh != 0, tanh.  HiFi-GAN's residual blocks need
+ * both x and leaky_relu(x); only y = leaky_relu(x, s) is stored and the residual read recovers x = min(y, y / s):
+ * res_neg_gain = 1 / s (1: the residual is stored as it is).  out bf16, or fp32 (out_fp32, contiguous). */
+int b200_conv1d(const void* x, int c, int nb, int len, int ntaps, int dh0, int dh_step, int m_rows, const void* wpacked,
+                int n_pad, int n_valid, const float* bias, const void* residual, int res_ld, float res_neg_gain, void* out,
+                int out_ld, long out_batch_stride, int out_fp32, float act_slope, int act_tanh, int block_n, int cta_pair,
+                void* stream);
+
+/* y = leaky_relu((x0 + x1 + x2) / 3, out_slope) over n bf16 elements, where the three inputs are stored as
+ * a_i = leaky_relu(x_i, in_slope): the mean over the three residual blocks of a HiFi-GAN upsampling stage and the
+ * activation in front of the next layer (SpeechT5HifiGan.forward). */
+int b200_lrelu_mean3(const void* a0, const void* a1, const void* a2, long n, float in_slope, float out_slope, void* y,
+                     void* stream);
+
+/* fp32 -> bf16 copy (the VAE decoder's fp32 log-mel as the vocoder's bf16 input). */
+int b200_f32_to_bf16(const float* x, long n, void* y, void* stream);
+
 /* Linear layer with the rank-r LoRA branch computed inside the kernel (peft lora.Linear, unmerged; LoRA config at
  * generate_audio.py:21-29, train_audioldm_lora.py:378-385):  out = x W^T + (x A^T)(s B)^T (+ bias + residual).
  * Phase 0 of every tile runs T = x A^T as a second, narrow tcgen05.mma into spare TMEM columns; the epilogue warps turn

@@ -425,5 +425,49 @@ def install(monkeypatch, ops_module):
     """Replace the kernel wrappers of `ops_module` (keeps PackedWeight / tiling helpers)."""
     for name in ("conv_gemm", "groupnorm_silu", "layernorm", "attention", "time_class_embed",
                  "pack_nchw_to_nhwc", "unpack_nhwc_to_nchw", "upsample_nearest", "sampler_step", "add_noise",
-                 "adamw_flat", "mse_partial", "set_sm_budget", "gn_stat_slabs", "groupnorm_apply", "linear_lora_ok", "linear_lora", "linear_ln", "linear_stats") + TRAIN_OPS:
+                 "adamw_flat", "mse_partial", "set_sm_budget", "gn_stat_slabs", "groupnorm_apply", "linear_lora_ok", "linear_lora", "linear_ln", "linear_stats",
+                 "conv1d", "lrelu_mean3", "f32_to_bf16") + TRAIN_OPS:
         monkeypatch.setattr(ops_module, name, globals()[name])
+
+
+# ------------------------------------------------------------------------------------------ HiFi-GAN vocoder
+def conv1d(pw, x, nb, length, out, *, dh0, dh_step, m_rows=None, residual=None, res_slope=1.0, act_slope=1.0,
+           act_tanh=False, out_ld=None, out_batch_stride=0, cta_pair=None):
+    """b200_conv1d semantics: out[n, q] = act(bias + sum_t x[n, q + dh0 + t dh_step] W_t^T + unact(residual[n, q]))."""
+    rows = length if m_rows is None else m_rows
+    c = pw.c0
+    xf = x.view(nb, length, c).float()
+    acc = torch.zeros(nb, rows, pw.n_pad)
+    wk = pw.w.float().view(pw.n_pad, pw.ntaps, c)
+    q = torch.arange(rows)
+    for t in range(pw.ntaps):
+        src = q + dh0 + t * dh_step
+        ok = (src >= 0) & (src < length)
+        g = torch.zeros(nb, rows, c)
+        g[:, ok] = xf[:, src[ok]]
+        acc += g @ wk[:, t].T
+    if pw.bias is not None:
+        acc = acc + pw.bias
+    acc = acc[..., :pw.n_valid]
+    if residual is not None:
+        r = residual.view(nb, length, pw.n_valid).float()
+        acc = acc + torch.minimum(r, r / res_slope)
+    acc = torch.tanh(acc) if act_tanh else torch.maximum(acc, acc * act_slope)
+    ld = out_ld if out_ld is not None else pw.n_valid
+    bs = out_batch_stride if out_batch_stride else rows * ld
+    flat = out.view(-1)
+    idx = (torch.arange(nb)[:, None, None] * bs + torch.arange(rows)[None, :, None] * ld + torch.arange(pw.n_valid)[None, None, :])
+    flat[idx.reshape(-1)] = acc.reshape(-1).to(out.dtype)
+    return out
+
+
+def lrelu_mean3(a0, a1, a2, in_slope, out_slope, y):
+    xs = [torch.minimum(a.float(), a.float() / in_slope) for a in (a0, a1, a2)]
+    m = (xs[0] + xs[1] + xs[2]) / 3.0
+    y.copy_(torch.maximum(m, m * out_slope).to(y.dtype))
+    return y
+
+
+def f32_to_bf16(x, y):
+    y.copy_(x.to(y.dtype))
+    return y
