@@ -128,17 +128,30 @@ struct ConvGemmParams {
                                     // stream (b200_gemm_nt): its producer warp must wait for that grid like everyone else
 };
 
-// exact-erf GELU to ~2e-7 absolute (Abramowitz-Stegun 7.1.26 erfc; bf16 output rounding is 4e-3 relative):
-//   gelu(g) = g/2 (1 + erf(g/sqrt2));  erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1/(1 + p z)
+// exact-erf GELU to ~7e-7 absolute (bf16 output rounding is 4e-3 relative), ONE MUFU op per element.  With s = |g|:
+//   gelu(g) = g/2 (1 + erf(g/sqrt2)) = relu(g) - s/2 erfc(s/sqrt2),
+//   erfc(x) = (1 + a1 x + ... + a6 x^6)^-16 + eps, |eps| <= 3e-7          (Abramowitz-Stegun 7.1.28)
+// the 1/sqrt2 is folded into the coefficients.  The form it replaced (A-S 7.1.26: a reciprocal AND an exponential, plus
+// the non-ftz range fix-ups of __fdividef / __expf: ~25 instructions, 2 MUFU) made the GEGLU epilogue XU-pipe-bound
+// (ncu: xu 64 % of peak, tensor pipe 4 %: profiles/r02_prof_geglu_l1.md); this one is 13 FP instructions + 1 MUFU.
 __device__ __forceinline__ float gelu_erf(float g) {
-  const float z = fabsf(g) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = poly * t * __expf(-z * z);
-  return g >= 0.f ? g * fmaf(-0.5f, e, 1.0f) : 0.5f * g * e;
+  const float s = fabsf(g);
+  constexpr float c1 = 0.0705230784f * 0.70710678118654752f;
+  constexpr float c2 = 0.0422820123f * 0.5f;
+  constexpr float c3 = 0.0092705272f * 0.35355339059327376f;
+  constexpr float c4 = 0.0001520143f * 0.25f;
+  constexpr float c5 = 0.0002765672f * 0.17677669529663688f;
+  constexpr float c6 = 0.0000430638f * 0.125f;
+  float p = fmaf(c6, s, c5);
+  p = fmaf(p, s, c4);
+  p = fmaf(p, s, c3);
+  p = fmaf(p, s, c2);
+  p = fmaf(p, s, c1);
+  p = fmaf(p, s, 1.0f);
+  p *= p; p *= p; p *= p; p *= p;                                // ^16 (inf for |g| > ~60: rcp -> 0, erfc -> 0)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+  return fmaf(-0.5f * s, r, fmaxf(g, 0.f));
 }
 
 // debug timeline (B200_GEMM_DEBUG & 4): SM cycle counter of CTA 0 at fixed points of the kernel
