@@ -54,7 +54,8 @@ static constexpr int kEpiWarps = 8;
 static constexpr int kProducerBWarp = 2 + kEpiWarps;    // the weight (B) TMA stream has its own warp
 static constexpr int kThreads = 64 + kEpiWarps * 32 + 32;   // warp0 TMA (A), warp1 MMA, warps2-9 epilogue, warp10 TMA (B)
 static constexpr int kEpiStageBytes = 32 * 128;         // per-warp staging: 32 rows x 64 bf16
-static constexpr int kEpiVecBytes = 128 * 4;            // per-warp scratch (row statistics of the LayerNorm-folded form)
+static constexpr int kEpiVecBytes = 256 * 4;            // per-warp scratch: (bias + per-image row vector) of the warp's output columns
+static constexpr int kBarrierBytes = 512;
 static constexpr int kSmemLimit = 227 * 1024;
 
 struct ConvGemmParams {
@@ -124,6 +125,11 @@ struct ConvGemmParams {
   float act_slope;
   float res_neg_gain;
   int act_tanh;
+  // Epilogue inputs staged instead of fetched per thread (each costs a launch 2-8 us when read with per-row LDGs after the
+  // accumulator is complete: gpurun_out/r02_res_ab.log): the residual tile comes by TMA into the warp's output staging
+  // buffers (two per warp then: epi_bufs) while the main loop still runs.
+  int res_tma;                      // 1: residual through tmRes
+  int epi_bufs;                     // staging buffers per epilogue warp (1, or 2 with res_tma)
   int b_dynamic;                    // 1: the "weight" operand is an activation written by the previous kernel in the
                                     // stream (b200_gemm_nt): its producer warp must wait for that grid like everyone else
 };
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(B200_GEMM_LB_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmLA,
-                 const ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmRes, const ConvGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024B alignment for the 128B swizzle atoms.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -221,14 +227,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int stage_bytes = kABytes + b_rows * kBlockK * 2;
   uint8_t* t_tile = smem + p.stages * stage_bytes;                 // [128 rows][64 bf16], 128B-swizzled (fused LoRA only)
   uint8_t* epi_smem = t_tile + (kLora ? kABytes : 0);
-  [[maybe_unused]] float* epi_vec = reinterpret_cast<float*>(epi_smem + kEpiWarps * kEpiStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * (kEpiStageBytes + kEpiVecBytes));
+  float* epi_vec = reinterpret_cast<float*>(epi_smem + kEpiWarps * p.epi_bufs * kEpiStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiWarps * (p.epi_bufs * kEpiStageBytes + kEpiVecBytes));
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* lt_tmem_bar = tempty_bar + 2;                          // phase-0 accumulator complete (MMA -> epilogue warps)
   uint64_t* lt_smem_bar = lt_tmem_bar + 1;                         // T tile written (4 epilogue warps -> MMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lt_smem_bar + 1);
+  uint64_t* res_bar = lt_smem_bar + 1;                             // [kEpiWarps][2]: residual tile landed in the warp's staging buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -241,6 +248,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB);
     if (p.tma_out) tma_prefetch_desc(&tmOut);
+    if (p.res_tma) tma_prefetch_desc(&tmRes);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 2);    // one arrive.expect_tx per producer thread
       mbar_init(&empty_bar[s], 1);
@@ -251,6 +259,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     mbar_init(lt_tmem_bar, 1);
     mbar_init(lt_smem_bar, 4);
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     if (kLora) tma_prefetch_desc(&tmLA);
     fence_barrier_init();
   }
@@ -560,8 +569,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int q_w = (q * 32) % p.W;
     const int q_h = ((q * 32) / p.W) % p.BH;
     const int q_n = (q * 32) / (p.W * p.BH);
-    uint8_t* stage = epi_smem + (warp - 2) * kEpiStageBytes;
-    const uint32_t stage_row = smem_u32(stage) + lane * 128;
+    uint8_t* stage0 = epi_smem + (warp - 2) * p.epi_bufs * kEpiStageBytes;
+    float* vec = epi_vec + (warp - 2) * (kEpiVecBytes / 4);
+    uint64_t* my_res_bar = res_bar + 2 * (warp - 2);
+    uint32_t res_ph0 = 0, res_ph1 = 0;
+    // (bias + row vector) of the warp's columns go through `vec` when the warp's 32 rows lie in one image
+    // TMA-store path (no folded LayerNorm): (bias + per-image row vector) of the warp's columns are staged in `vec` at the top of
+    // every tile, unconditionally (zeros without a bias).  The row vector joins them when the warp's 32 rows lie in one image
+    // (always, except for images of fewer than 32 pixels); otherwise it is fetched per thread.
+    const bool use_vec = !kLn && p.tma_out;
+    const bool rv_vec = p.rowvec != nullptr && (p.W * p.BH) % 32 == 0;
     const int half = p.block_n / 2;
     const int out_cols = p.geglu ? half : p.block_n;     // output columns per tile
     int it = 0;
@@ -649,6 +666,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(lt_smem_bar);
       }
+      if (p.res_tma) {
+        // ---- residual tiles of this warp's chunks: TMA into the staging buffers, in flight while the main loop runs
+        if (lane == 0) {
+          tma_store_wait_read<0>();                    // the previous tile's stores have finished reading the buffers
+          for (int i = 0; hf + 2 * i < nchunks; ++i) {
+            mbar_expect_tx(&my_res_bar[i], static_cast<uint32_t>(kEpiStageBytes));
+            tma_load_4d(stage0 + i * kEpiStageBytes, &tmRes, &my_res_bar[i], n_tile * out_cols + (hf + 2 * i) * 64, q_w, h_t + q_h,
+                        n_t + q_n);
+          }
+        }
+      }
+      if (use_vec) {
+        const int n_w = n_t + q_n;                     // image of this warp's rows
+        for (int i = 0; hf + 2 * i < nchunks; ++i) {
+          const int cc = hf + 2 * i;
+          if (!p.geglu) {
+            const int col = n_tile * out_cols + cc * 64 + 2 * lane;
+            float2 b = p.bias ? *reinterpret_cast<const float2*>(p.bias + col) : make_float2(0.f, 0.f);
+            if (rv_vec && n_w < p.NB && col < p.n_valid) {
+              const float2 r = *reinterpret_cast<const float2*>(p.rowvec + static_cast<size_t>(n_w) * p.rowvec_ld + col);
+              b.x += r.x; b.y += r.y;
+            }
+            *reinterpret_cast<float2*>(vec + i * 64 + 2 * lane) = b;
+          } else {
+            const int bcol = n_tile * p.block_n + cc * 64 + 2 * lane;
+            const float2 z = make_float2(0.f, 0.f);
+            *reinterpret_cast<float2*>(vec + i * 128 + 2 * lane) = p.bias ? *reinterpret_cast<const float2*>(p.bias + bcol) : z;
+            *reinterpret_cast<float2*>(vec + i * 128 + 64 + 2 * lane) = p.bias ? *reinterpret_cast<const float2*>(p.bias + bcol + half) : z;
+          }
+        }
+        __syncwarp();
+      }
       mbar_wait(&tfull_bar[buf], use & 1);
       if (warp == 2 && lane == 0) TL(12);
       tc_fence_after();
@@ -656,6 +705,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (p.tma_out) {
         // -------- bf16, stride 1: 64-column chunks -> swizzled smem -> TMA store
         for (int cc = hf; cc < nchunks; cc += 2) {
+          const int ci = cc >> 1;                          // this warp's ci-th chunk of the tile
+          uint8_t* stage = stage0 + (p.epi_bufs == 2 ? ci * kEpiStageBytes : 0);
+          const uint32_t stage_row = smem_u32(stage) + lane * 128;
+          if (p.res_tma) {
+            if (ci == 0) { mbar_wait(&my_res_bar[0], res_ph0); res_ph0 ^= 1; }
+            else { mbar_wait(&my_res_bar[1], res_ph1); res_ph1 ^= 1; }
+          }
           uint32_t pk[32];
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
@@ -672,11 +728,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
                 const int cg = gcol + g * 8;
                 if (kLn) ln_affine8(v, p.ln_g + cg, p.bias + cg, ln_mu, ln_rs);
-                else if (p.bias) add8(v, p.bias + cg);
+                else add8(v, vec + ci * 64 + hh * 32 + g * 8);
                 if (row_ok && cg < p.n_valid) {
-                  if (p.rowvec) add8(v, p.rowvec + static_cast<size_t>(n) * p.rowvec_ld + cg);
-                  if (p.residual) {
-                    const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + pix * p.res_ld + cg);
+                  if (p.rowvec && (kLn || !rv_vec)) add8(v, p.rowvec + static_cast<size_t>(n) * p.rowvec_ld + cg);
+                  if (p.res_tma) {
+                    uint4 rr;             // this thread's row of the residual tile the TMA left in the staging buffer
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w)
+                                 : "r"(stage_row + (((hh * 4 + g) ^ (lane & 7)) << 4)));
                     if (kAct) add_res8_unact(v, rr, p.res_neg_gain);
                     else {
                       v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
@@ -706,9 +764,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 if (kLn) {
                   ln_affine8(v, p.ln_g + bcol + g * 8, p.bias + bcol + g * 8, ln_mu, ln_rs);
                   ln_affine8(gt, p.ln_g + bcol + half + g * 8, p.bias + bcol + half + g * 8, ln_mu, ln_rs);
-                } else if (p.bias) {
-                  add8(v, p.bias + bcol + g * 8);
-                  add8(gt, p.bias + bcol + half + g * 8);
+                } else {
+                  add8(v, vec + ci * 128 + hh * 32 + g * 8);
+                  add8(gt, vec + ci * 128 + 64 + hh * 32 + g * 8);
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] *= gelu_erf(gt[j]);
@@ -730,9 +788,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int gchunk = (n_tile * out_cols + cc * 64) >> 6;
             reinterpret_cast<float2*>(p.stat_out)[pix * p.stat_chunks + gchunk] = make_float2(sx, sq);
           }
-          // the previous TMA store of this warp must have finished reading the staging tile
-          if (lane == 0) tma_store_wait_read<0>();
-          __syncwarp();
+          // the previous TMA store of this warp must have finished reading the staging tile (res_tma: waited at the tile's top)
+          if (!p.res_tma) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const uint32_t addr = stage_row + ((g ^ (lane & 7)) << 4);
@@ -1155,7 +1215,9 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
   p.num_m_groups = cta2 ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
   const int b_rows = cta2 ? block_n / 2 : block_n;
   const int stage_bytes = kABytes + b_rows * kBlockK * 2;
-  const int fixed = kEpiWarps * (kEpiStageBytes + kEpiVecBytes) + 1024 /*align slack*/ + 256 /*barriers*/ +
+  p.res_tma = (p.residual != nullptr && p.tma_out) ? 1 : 0;          // (the direct-store path keeps per-thread loads)
+  p.epi_bufs = p.res_tma ? 2 : 1;
+  const int fixed = kEpiWarps * (p.epi_bufs * kEpiStageBytes + kEpiVecBytes) + 1024 /*align slack*/ + kBarrierBytes +
                     (fused_lora ? kABytes : 0) /*T tile*/;
   // B200_GEMM_SMEM_KB: shared memory this kernel may take (default: all 227 KB).  Less leaves room for the CTAs of the
   // neighbouring kernels in the stream to become resident early (programmatic dependent launch).
@@ -1169,7 +1231,7 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
   p.debug = dbg_flags;
   const int smem_bytes = p.stages * stage_bytes + fixed;
 
-  CUtensorMap tA[3], tB, tO, tLA;
+  CUtensorMap tA[3], tB, tO, tLA, tR;
   const void* srcs[3] = {a0, a1 ? a1 : a0, a2 ? a2 : a0};
   const int chans[3] = {c0, c1 ? c1 : c0, c2 ? c2 : c0};
   p.a_rank2 = 0;     // plain 2-D maps for linear layers were measured: no difference to the 4-D box
@@ -1221,6 +1283,21 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
   } else {
     tO = tB;
   }
+  if (p.res_tma) {
+    // same boxes as the output store, over the residual tensor
+    const int bw = w < 32 ? w : 32;
+    int bh = 32 / bw;
+    if (bh > p.BH) bh = p.BH;
+    const int bn = 32 / (bw * bh);
+    const uint64_t L = res_ld;
+    uint64_t dims[4] = {(uint64_t)n_valid, (uint64_t)w, (uint64_t)m_h, (uint64_t)nb};
+    uint64_t strides[3] = {L, L * w, L * w * m_h};
+    uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+    int rc = make_tmap_bf16(&tR, residual, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  } else {
+    tR = tB;
+  }
 
   static int num_sms = 0;
   if (!num_sms) {
@@ -1246,40 +1323,40 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
     if (grid < 1) grid = 1;
     if (c1d)
       B200_CHECK_PDL("conv1d(2-CTA)", launch_pdl(conv_gemm_kernel<true, false, false, false, false, true>, dim3(2 * grid),
-                                                 dim3(kThreads), (size_t)smem_bytes, stream, 2, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+                                                 dim3(kThreads), (size_t)smem_bytes, stream, 2, tA[0], tA[1], tA[2], tB, tO, tLA, tR, p));
     else if (gn_stat)
       B200_CHECK_PDL("conv_gemm_gnstat(2-CTA)", launch_pdl(conv_gemm_kernel<true, false, false, false, true>, dim3(2 * grid),
                                                            dim3(kThreads), (size_t)smem_bytes, stream, 2, tA[0], tA[1], tA[2], tB,
-                                                           tO, tLA, p));
+                                                           tO, tLA, tR, p));
     else
       B200_CHECK_PDL("conv_gemm(2-CTA)", launch_pdl(conv_gemm_kernel<true, false>, dim3(2 * grid), dim3(kThreads), (size_t)smem_bytes,
-                                                    stream, 2, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+                                                    stream, 2, tA[0], tA[1], tA[2], tB, tO, tLA, tR, p));
   } else {
     if (grid > cap) grid = cap;
     if (c1d)
       B200_CHECK_PDL("conv1d", launch_pdl(conv_gemm_kernel<false, false, false, false, false, true>, dim3(grid), dim3(kThreads),
-                                               (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+                                               (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, tR, p));
     else if (gn_stat)
       B200_CHECK_PDL("conv_gemm_gnstat", launch_pdl(conv_gemm_kernel<false, false, false, false, true>, dim3(grid), dim3(kThreads),
-                                                    (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+                                                    (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, tR, p));
     else if (stat_out && !fused_ln && fused_lora)
       B200_CHECK_PDL("linear_stats(lora)", launch_pdl(conv_gemm_kernel<false, true, false, true>, dim3(grid), dim3(kThreads),
-                                                      (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+                                                      (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, tR, p));
     else if (stat_out && !fused_ln)
       B200_CHECK_PDL("linear_stats", launch_pdl(conv_gemm_kernel<false, false, false, true>, dim3(grid), dim3(kThreads),
-                                                (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+                                                (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, tR, p));
     else if (fused_lora && fused_ln)
       B200_CHECK_PDL("linear_ln(lora)", launch_pdl(conv_gemm_kernel<false, true, true>, dim3(grid), dim3(kThreads),
-                                                   (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+                                                   (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, tR, p));
     else if (fused_ln)
       B200_CHECK_PDL("linear_ln", launch_pdl(conv_gemm_kernel<false, false, true>, dim3(grid), dim3(kThreads),
-                                             (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+                                             (size_t)smem_bytes, stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, tR, p));
     else if (fused_lora)
       B200_CHECK_PDL("linear_lora", launch_pdl(conv_gemm_kernel<false, true>, dim3(grid), dim3(kThreads), (size_t)smem_bytes,
-                                               stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+                                               stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, tR, p));
     else
       B200_CHECK_PDL("conv_gemm", launch_pdl(conv_gemm_kernel<false, false>, dim3(grid), dim3(kThreads), (size_t)smem_bytes,
-                                             stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, p));
+                                             stream, 0, tA[0], tA[1], tA[2], tB, tO, tLA, tR, p));
   }
   if (p.ksplit > 1) {
     const size_t total = m_total * (n_valid / 8);

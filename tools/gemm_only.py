@@ -16,6 +16,7 @@ geglu = bool(int(a[4])) if len(a) > 4 else False
 bn = int(a[5]) if len(a) > 5 and a[5] != "auto" else None
 pair = None if len(a) <= 6 or a[6] == "auto" else bool(int(a[6]))
 reps = int(a[7]) if len(a) > 7 else 50
+extra = a[8] if len(a) > 8 else ""            # any of: r (residual), v (per-image row vector = the temb add)
 c = K // taps
 if taps == 9:
     nb = 16
@@ -32,15 +33,18 @@ if bn is None:
 pw = packing.pack([wt], torch.zeros(n_gemm), bn, taps, c, geglu=geglu, device="cuda")
 x = torch.randn(nb * h * w, c, device="cuda").to(torch.bfloat16)
 out = torch.empty(nb * h * w, N, dtype=torch.bfloat16, device="cuda")
+res = torch.randn(nb * h * w, N, device="cuda").to(torch.bfloat16) if "r" in extra else None
+rv = torch.randn(nb, N, device="cuda") if "v" in extra else None
+kw = dict(cta_pair=pair, residual=res, rowvec=rv, rowvec_ld=N if rv is not None else 0)
 for _ in range(5):
-    ops.conv_gemm(pw, x, nb, h, w, out, cta_pair=pair)
+    ops.conv_gemm(pw, x, nb, h, w, out, **kw)
 torch.cuda.synchronize()
 g = torch.cuda.CUDAGraph()
 with torch.cuda.graph(g):
     for _ in range(reps):
-        ops.conv_gemm(pw, x, nb, h, w, out, cta_pair=pair)
+        ops.conv_gemm(pw, x, nb, h, w, out, **kw)
 g.replay(); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / reps * 1e3
-print(f"M={M} N={N} K={K} taps={taps} geglu={int(geglu)} bn={bn} pair={pair}: {us:.2f} us  {2.0 * M * n_gemm * K / us / 1e6:.0f} TFLOP/s")
+print(f"M={M} N={N} K={K} taps={taps} geglu={int(geglu)} bn={bn} pair={pair} extra={extra!r}: {us:.2f} us  {2.0 * M * n_gemm * K / us / 1e6:.0f} TFLOP/s")
