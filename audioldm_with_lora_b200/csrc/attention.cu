@@ -39,7 +39,7 @@ static constexpr float kRescaleThreshold = 8.0f;   // move the reference maximum
 struct AttnParams {
   int seq, heads, d, batch;
   int nblk;                 // ceil(seq / 128)
-  int stages;               // K/V ring depth (1 or 2)
+  int stages;               // K/V ring depth (1 .. 4)
   int tmem_cols;            // 256 (d + 16 <= 128) or 512
   float scale_log2;         // scale * log2(e)
   __nv_bfloat16* out;
@@ -138,6 +138,15 @@ __device__ __forceinline__ void scale_o(uint32_t t_o_row, int ncols, float f) {
   tmem_wait_st();
 }
 
+// -DB200_ATTN_PROFILE=1 builds only (tools/build_variant.sh attnprof -DB200_ATTN_PROFILE=1; tools/attn_timeline.py): cycle
+// stamps of CTA (0, 0), printed by the kernel itself
+#if B200_ATTN_PROFILE
+__device__ long long s_tl[48];
+#define ATL(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) s_tl[i] = clock64(); } while (0)
+#else
+#define ATL(i) do {} while (0)
+#endif
+
 template <int D, int KV>
 __global__ void __launch_bounds__(kAttnThreads)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
@@ -156,15 +165,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   uint8_t* sKV = sP + kPBytes;                  // stages x {K, V, ones}
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + p.stages * kStageBytes);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;                 // [2]
-  uint64_t* kv_empty = bars + 3;                // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* kv_full = bars + 1;                 // [4]
+  uint64_t* kv_empty = bars + 5;                // [4]
+  uint64_t* s_full = bars + 9;
+  uint64_t* p_full = bars + 10;
+  uint64_t* o_full = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (warp == 0) ATL(0);
   const int q0 = blockIdx.x * kQ;
   const int bh = blockIdx.y;
   const int b = bh / p.heads;
@@ -177,7 +187,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
@@ -201,8 +211,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) ATL(1);
   pdl_launch_dependents();
   pdl_wait();
+  if (warp == 0) ATL(2);
   const uint32_t t_s = tmem_base;               // S: columns [0, KV)
   const uint32_t t_o = tmem_base + KV;          // O: columns [KV, KV + D + 16)
 
@@ -252,6 +264,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         const uint32_t v_addr = k_addr + kKVTile;
         mbar_wait(&kv_full[s], ph);
         tc_fence_after();
+        if (j < 4) ATL(8 + j);                  // K/V block j landed
         // S = Q K^T   (the previous block's softmax finished reading S before it released p_full)
         if (elect_one()) {
 #pragma unroll
@@ -299,6 +312,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       const bool full = kvalid == kKV;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      if (warp == 0 && j < 4) ATL(16 + j);      // S_j complete
       if (j == 0) {
         const float mx = full ? row_max<false, KV>(t_s + lane_off, kvalid) : row_max<true, KV>(t_s + lane_off, kvalid);
         ref = mx * p.scale_log2;
@@ -328,9 +342,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
+      if (warp == 0 && j < 4) ATL(24 + j);      // P_j written
+      if (warp == 0 && j == p.nblk - 1) ATL(32);
     }
     mbar_wait(o_full, (p.nblk - 1) & 1);
     tc_fence_after();
+    if (warp == 0) ATL(33);                     // last P V complete
     // epilogue: O[:, :d] / O[:, d]
     const int qrow = q0 + row;
     uint32_t rl[16];
@@ -360,11 +377,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     tc_fence_before();
   }
 
+  if (warp == 0) ATL(34);                       // output rows stored
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+#if B200_ATTN_PROFILE
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    const long long t0 = s_tl[0];
+    printf("attn<%d,%d> nblk %d stages %d: prologue %lld  pdl_wait %lld | kv0 %lld kv1 %lld kv2 %lld kv3 %lld | S0 %lld S1 %lld S2 %lld S3 %lld | "
+           "P0 %lld P1 %lld P2 %lld P3 %lld | lastP %lld lastPV %lld stored %lld end %lld\n", D, KV, p.nblk, p.stages, s_tl[1] - t0, s_tl[2] - t0,
+           s_tl[8] - t0, s_tl[9] - t0, s_tl[10] - t0, s_tl[11] - t0, s_tl[16] - t0, s_tl[17] - t0, s_tl[18] - t0, s_tl[19] - t0,
+           s_tl[24] - t0, s_tl[25] - t0, s_tl[26] - t0, s_tl[27] - t0, s_tl[32] - t0, s_tl[33] - t0, s_tl[34] - t0,
+           (long long)clock64() - t0);
+  }
+#endif
 }
 
 template <int D, int KV>
@@ -372,10 +400,21 @@ static int launch_attention(const CUtensorMap& tm, const CUtensorMap& tmkv, Attn
   constexpr int kTileBytes = 128 * D * 2;
   constexpr int kStageBytes = 2 * KV * D * 2 + 2 * KV * 16;
   const int fixed = kTileBytes + kQ * KV * 2 + 128 /*barriers*/ + 128 /*align*/;
-  // resident CTAs per SM are set by TMEM: 512 / tmem_cols (4, 2 or 1); give each its share of shared memory
-  const int per_sm = 512 / p.tmem_cols;
-  const int budget = (220 * 1024) / per_sm;
-  p.stages = (fixed + 2 * kStageBytes <= budget) ? 2 : 1;
+  // resident CTAs per SM are set by TMEM: 512 / tmem_cols (4, 2 or 1); give each its share of shared memory.  The K/V
+  // ring wants >= 2 stages: with one, the next block's loads start only after the current block's P V has completed (the
+  // CTA timeline showed exactly that at head_dim 48: profiles/r02_attn_timeline.md), so a fourth co-resident CTA is given
+  // up when its share of shared memory would leave a single stage.
+  int per_sm = 512 / p.tmem_cols;
+  int budget = (220 * 1024) / per_sm;
+  if (per_sm >= 4 && fixed + 2 * kStageBytes > budget) {
+    --per_sm;
+    budget = (220 * 1024) / per_sm;
+  }
+  p.stages = (budget - fixed) / kStageBytes;
+  if (p.stages > 4) p.stages = 4;
+  if (p.stages < 1) p.stages = 1;
+  static const int dbg_stages = getenv("B200_ATTN_STAGES") ? atoi(getenv("B200_ATTN_STAGES")) : 0;       // A/B knob
+  if (dbg_stages > 0 && dbg_stages < p.stages) p.stages = dbg_stages;
   const int smem_bytes = fixed + p.stages * kStageBytes;
   static bool configured = false;
   if (!configured) {
