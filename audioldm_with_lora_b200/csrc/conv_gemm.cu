@@ -77,8 +77,8 @@ struct ConvGemmParams {
   int out_fp32;
   int geglu;
   int tmem_cols;
-  int stride;                       // 1, or 2: keep even (h, w) only (Downsample2D: k3 s2 p1)
-  int Hout, Wout;
+  int a_stride;                     // 1, or 2 (Downsample2D: k3 s2 p1): the activation box is read with TMA element strides (2, 2),
+                                    //   the tile's 128 rows are OUTPUT pixels and H / W / tiles_h describe the output
   int tma_out;                      // 1: bf16 stride-1 output through smem staging + TMA store
   int num_m_groups;                 // m-tiles (1-CTA) or pairs of m-tiles (2-CTA) the tile index runs over
   int ksplit;                       // > 1: split-K; work item = (split, m_tile, n_tile), fp32 partials to `out`
@@ -350,7 +350,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int end0 = min(kb_end, seg_end0);
         {
           int left = cb0 - cb;              // k-blocks left in the current tap
-          int c = cb * kBlockK, hh = h0 + dh;
+          int c = cb * kBlockK, hh = h0 * p.a_stride + dh;
 #pragma unroll 1
           for (; kb < end0; ++kb) {
             acquire();
@@ -559,8 +559,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else {
     // ================================================================ epilogue warps
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int hf = (warp - 2) >> 2;         // which of the two warps of the quarter: takes chunks cc % 2 == hf
+    // (warp index through a lane-0 broadcast: the compiler then KNOWS that everything derived from it -- TMA coordinates,
+    //  staging addresses, chunk loops -- is warp-uniform, and an elected lane can issue the epilogue's TMA loads / stores
+    //  without an ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall in front of each)
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const int q = warp_u & 3;               // TMEM lane quarter this warp may access
+    const int hf = (warp_u - 2) >> 2;       // which of the two warps of the quarter: takes chunks cc % 2 == hf
     const int row = q * 32 + lane;          // accumulator row == tile pixel
     const int wl = row % p.W;
     const int hl = (row / p.W) % p.BH;
@@ -569,9 +573,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int q_w = (q * 32) % p.W;
     const int q_h = ((q * 32) / p.W) % p.BH;
     const int q_n = (q * 32) / (p.W * p.BH);
-    uint8_t* stage0 = epi_smem + (warp - 2) * p.epi_bufs * kEpiStageBytes;
-    float* vec = epi_vec + (warp - 2) * (kEpiVecBytes / 4);
-    uint64_t* my_res_bar = res_bar + 2 * (warp - 2);
+    uint8_t* stage0 = epi_smem + (warp_u - 2) * p.epi_bufs * kEpiStageBytes;
+    float* vec = epi_vec + (warp_u - 2) * (kEpiVecBytes / 4);
+    uint64_t* my_res_bar = res_bar + 2 * (warp_u - 2);
     uint32_t res_ph0 = 0, res_ph1 = 0;
     // (bias + row vector) of the warp's columns go through `vec` when the warp's 32 rows lie in one image
     // TMA-store path (no folded LayerNorm): (bias + per-image row vector) of the warp's columns are staged in `vec` at the top of
@@ -593,12 +597,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int n_t = (m_tile / p.tiles_h) * p.BNI;
       const int h = h_t + hl;
       const int n = n_t + nl;
-      bool row_ok = (h < p.H) && (n < p.NB);
-      size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + wl;
-      if (p.stride == 2) {
-        row_ok = row_ok && ((h & 1) == 0) && ((wl & 1) == 0);
-        pix = (static_cast<size_t>(n) * p.Hout + (h >> 1)) * p.Wout + (wl >> 1);
-      }
+      const bool row_ok = (h < p.H) && (n < p.NB);
+      const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + wl;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * p.block_n;
       const int nchunks = p.tma_out ? (out_cols >> 6) : 0;
       [[maybe_unused]] float ln_mu = 0.f, ln_rs = 0.f;
@@ -668,9 +668,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       if (p.res_tma) {
         // ---- residual tiles of this warp's chunks: TMA into the staging buffers, in flight while the main loop runs
-        if (lane == 0) {
-          tma_store_wait_read<0>();                    // the previous tile's stores have finished reading the buffers
-          for (int i = 0; hf + 2 * i < nchunks; ++i) {
+        // (bulk-store groups belong to the thread that committed them: elect.sync picks the same lane every time)
+        if (elect_one()) tma_store_wait_read<0>();     // the previous tile's stores have finished reading the buffers
+        for (int i = 0; hf + 2 * i < nchunks; ++i) {
+          if (elect_one()) {
             mbar_expect_tx(&my_res_bar[i], static_cast<uint32_t>(kEpiStageBytes));
             tma_load_4d(stage0 + i * kEpiStageBytes, &tmRes, &my_res_bar[i], n_tile * out_cols + (hf + 2 * i) * 64, q_w, h_t + q_h,
                         n_t + q_n);
@@ -721,6 +722,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (!p.geglu) {
               tmem_ld_x32(t_row + oc, r);
               tmem_wait_ld();
+              if (warp == 2 && lane == 0 && it == 0 && cc == 0 && hh == 0) TL(17);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 float v[8];
@@ -775,6 +777,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               }
             }
           }
+          if (warp == 2 && lane == 0 && it == 0 && cc == 0) TL(16);
           if (kStat && row_ok && n_tile * out_cols + cc * 64 < p.n_valid) {
             // row statistics of the values being stored (after bf16 rounding): what the consuming LayerNorm-folded GEMM needs
             float sx = 0.f, sq = 0.f;
@@ -790,7 +793,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
           // the previous TMA store of this warp must have finished reading the staging tile (res_tma: waited at the tile's top)
           if (!p.res_tma) {
-            if (lane == 0) tma_store_wait_read<0>();
+            if (elect_one()) tma_store_wait_read<0>();
             __syncwarp();
           }
 #pragma unroll
@@ -800,12 +803,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                          "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3])
                          : "memory");
           }
+          if (warp == 2 && lane == 0 && it == 0 && cc == 0) TL(18);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             tma_store_4d(&tmOut, stage, n_tile * out_cols + cc * 64, q_w, h_t + q_h, n_t + q_n);
             tma_store_commit();
           }
+          if (warp == 2 && lane == 0 && it == 0 && cc == 0) TL(19);
           if (kGn) {
             // ---- GroupNorm partial statistics of this warp's 32 rows x 64 columns, read back TRANSPOSED from the staging
             //      tile (lane l owns columns 2l, 2l+1; the swizzle keeps the 32 lanes on 32 different banks), rows outside the
@@ -890,7 +895,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
     // smem may not be released while a bulk store still reads it; global visibility comes with grid completion
-    if (p.tma_out && lane == 0) tma_store_wait_read<0>();
+    if (p.tma_out && elect_one()) tma_store_wait_read<0>();
     if (warp == 2 && lane == 0) TL(14);
   }
   if (warp == 0 && lane == 0) TL(5);
@@ -1105,7 +1110,9 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
                           const float* ln_g, const float* ln_ga, const float* ln_ba, float ln_eps, const float* ln_stats,
                           float* stat_out, void* stream_v, float* gn_stat, int b_dynamic, const Conv1dOpts* c1d) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  const int m_h = c1d ? c1d->m_h : h;               // output rows per image
+  const bool s2 = stride == 2;                      // Downsample2D: computed at OUTPUT resolution (strided activation boxes)
+  const int m_h = s2 ? (h - 1) / 2 + 1 : (c1d ? c1d->m_h : h);     // output rows per image
+  const int w_o = s2 ? (w - 1) / 2 + 1 : w;         // output width
   const bool fused_lora = lora_down != nullptr;
   const bool fused_ln = ln_g != nullptr;
   if (fused_ln) {
@@ -1120,7 +1127,7 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
     B200_CHECK_ARG(2 * block_n + 64 <= 512, "linear_lora: block_n %d leaves no TMEM columns for T", block_n);
     cta_pair = 0;
   }
-  B200_CHECK_ARG(stride == 1 || (stride == 2 && ntaps == 9 && !residual), "conv_gemm: stride %d unsupported", stride);
+  B200_CHECK_ARG(stride == 1 || (stride == 2 && ntaps == 9 && c1 == 0 && c2 == 0), "conv_gemm: stride %d unsupported", stride);
   B200_CHECK_ARG(a0 && wpacked && out, "conv_gemm: null pointer");
   B200_CHECK_ARG(ntaps == 1 || ntaps == 9 || (c1d && ntaps >= 1 && ntaps <= 16), "conv_gemm: ntaps must be 1 or 9 (got %d)", ntaps);
   B200_CHECK_ARG(!c1d || (w == 1 && stride == 1 && ksplit <= 1 && !geglu && !fused_lora && !fused_ln && !stat_out && !gn_stat &&
@@ -1139,7 +1146,7 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
 
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
-  if (pick_box(m_h, w, nb, &p.BH, &p.BNI) != 0) return fail(B200_ERR_UNSUPPORTED, "conv_gemm: width %d does not divide 128", w);
+  if (pick_box(m_h, w_o, nb, &p.BH, &p.BNI) != 0) return fail(B200_ERR_UNSUPPORTED, "conv_gemm: width %d does not divide 128", w_o);
   if (c1d) {
     p.dh0 = c1d->dh0; p.dh_step = c1d->dh_step; p.dw0 = 0; p.dw_end = 1;
     p.act_slope = c1d->act_slope; p.res_neg_gain = c1d->res_neg_gain; p.act_tanh = c1d->act_tanh;
@@ -1153,10 +1160,8 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
   p.seg_end0 = ntaps * p.cb0;
   p.seg_end1 = p.seg_end0 + c1 / 64;
   p.num_kb = p.seg_end1 + c2 / 64;
-  p.H = m_h; p.W = w; p.NB = nb;          // the epilogue's geometry (== the input's except for b200_conv1d with m_h != h)
-  p.stride = stride;
-  p.Hout = stride == 2 ? (h - 1) / 2 + 1 : h;
-  p.Wout = stride == 2 ? (w - 1) / 2 + 1 : w;
+  p.H = m_h; p.W = w_o; p.NB = nb;        // the epilogue's geometry (== the input's except for stride 2 and b200_conv1d with m_h != h)
+  p.a_stride = s2 ? 2 : 1;
   p.tiles_h = (m_h + p.BH - 1) / p.BH;
   p.num_m_tiles = p.tiles_h * ((nb + p.BNI - 1) / p.BNI);
   p.num_n_tiles = n_pad / block_n;
@@ -1165,10 +1170,10 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
   p.bias = bias; p.rowvec = rowvec; p.rowvec_ld = rowvec_ld;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.res_ld = res_ld;
   p.out = out; p.out_ld = out_ld; p.out_fp32 = out_fp32; p.geglu = geglu;
-  p.tma_out = (!out_fp32 && stride == 1 && block_n % 64 == 0) ? 1 : 0;
+  p.tma_out = (!out_fp32 && block_n % 64 == 0) ? 1 : 0;
   p.ksplit = 1;
   p.kb_per_split = p.num_kb;
-  const size_t m_total = static_cast<size_t>(nb) * m_h * w;
+  const size_t m_total = static_cast<size_t>(nb) * m_h * w_o;
   if (ksplit > 1) {
     p.kb_per_split = (p.num_kb + ksplit - 1) / ksplit;
     p.ksplit = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;      // no empty splits
@@ -1246,8 +1251,15 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
     } else {
       uint64_t dims[4] = {C, (uint64_t)w, (uint64_t)h, (uint64_t)nb};
       uint64_t strides[3] = {C, C * w, C * w * h};
-      uint32_t box[4] = {64, (uint32_t)w, (uint32_t)p.BH, (uint32_t)p.BNI};
-      rc = make_tmap_bf16(&tA[i], srcs[i], 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (s2) {
+        // every second pixel in w and h: the box spans 2 w_o x 2 BH input pixels, of which w_o x BH are fetched
+        uint32_t box[4] = {64, (uint32_t)(2 * w_o), (uint32_t)(2 * p.BH), (uint32_t)p.BNI};
+        uint32_t es[4] = {1, 2, 2, 1};
+        rc = make_tmap_bf16_strided(&tA[i], srcs[i], 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+      } else {
+        uint32_t box[4] = {64, (uint32_t)w, (uint32_t)p.BH, (uint32_t)p.BNI};
+        rc = make_tmap_bf16(&tA[i], srcs[i], 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      }
     }
     if (rc) return rc;
   }
@@ -1270,13 +1282,13 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
   }
   if (p.tma_out) {
     // each epilogue warp stores its 32 accumulator rows x 64 columns: box = (64, bw, bh, bn), w fastest
-    const int bw = w < 32 ? w : 32;
+    const int bw = w_o < 32 ? w_o : 32;
     int bh = 32 / bw;
     if (bh > p.BH) bh = p.BH;
     const int bn = 32 / (bw * bh);
     const uint64_t L = out_ld;
-    uint64_t dims[4] = {(uint64_t)n_valid, (uint64_t)w, (uint64_t)m_h, (uint64_t)nb};
-    uint64_t strides[3] = {L, L * w, (c1d && c1d->out_batch_stride) ? (uint64_t)c1d->out_batch_stride : L * w * m_h};
+    uint64_t dims[4] = {(uint64_t)n_valid, (uint64_t)w_o, (uint64_t)m_h, (uint64_t)nb};
+    uint64_t strides[3] = {L, L * w_o, (c1d && c1d->out_batch_stride) ? (uint64_t)c1d->out_batch_stride : L * w_o * m_h};
     uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
     int rc = make_tmap_bf16(&tO, out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -1285,13 +1297,13 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
   }
   if (p.res_tma) {
     // same boxes as the output store, over the residual tensor
-    const int bw = w < 32 ? w : 32;
+    const int bw = w_o < 32 ? w_o : 32;
     int bh = 32 / bw;
     if (bh > p.BH) bh = p.BH;
     const int bn = 32 / (bw * bh);
     const uint64_t L = res_ld;
-    uint64_t dims[4] = {(uint64_t)n_valid, (uint64_t)w, (uint64_t)m_h, (uint64_t)nb};
-    uint64_t strides[3] = {L, L * w, L * w * m_h};
+    uint64_t dims[4] = {(uint64_t)n_valid, (uint64_t)w_o, (uint64_t)m_h, (uint64_t)nb};
+    uint64_t strides[3] = {L, L * w_o, L * w_o * m_h};
     uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
     int rc = make_tmap_bf16(&tR, residual, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -1364,7 +1376,7 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
     if (rgrid > num_sms * 8) rgrid = num_sms * 8;
     B200_CHECK_PDL("conv_gemm(split-K reduce)",
                    launch_pdl(splitk_reduce_kernel, dim3(rgrid), dim3(256), 0, stream, 0, workspace, p.ksplit,
-                              p.split_stride, (int)m_total, n_valid, n_pad, bias, rowvec, rowvec_ld, h * w,
+                              p.split_stride, (int)m_total, n_valid, n_pad, bias, rowvec, rowvec_ld, m_h * w_o,
                               reinterpret_cast<const __nv_bfloat16*>(residual), res_ld,
                               reinterpret_cast<__nv_bfloat16*>(out), out_ld));
   }

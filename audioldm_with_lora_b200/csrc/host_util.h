@@ -119,6 +119,29 @@ inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint
   return rc;
 }
 
+// Same with traversal (element) strides per dimension: every es[i]-th element of the box is fetched (Downsample2D's
+// stride-2 convolution reads every second pixel).  Not cached: three launches per step, all under graph replay.
+inline int make_tmap_bf16_strided(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                                  const uint32_t* box, const uint32_t* es_in, CUtensorMapSwizzle swz) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return fail(B200_ERR_DRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = es_in[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_el[i] * 2;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(B200_ERR_ARG, "TMA base not 16B aligned");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(B200_ERR_DRIVER, "cuTensorMapEncodeTiled (strided) failed: %d (box %u,%u,%u,%u)", (int)r, box[0], rank > 1 ? box[1] : 0,
+                rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+  return B200_OK;
+}
+
 inline int make_tmap_bf16_uncached(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
                                    const uint64_t* strides_el, const uint32_t* box, CUtensorMapSwizzle swz) {
   PFN_encodeTiled fn = get_encode_fn();

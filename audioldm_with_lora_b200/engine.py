@@ -209,9 +209,9 @@ class UNetEngine:
             hh, ww = sizes[lvl]
             return math.ceil(nb * hh * ww / 128)
 
-        def conv3(name, lvl, c_pad=None):
+        def conv3(name, lvl, c_pad=None, tiles_lvl=None):
             wk = packing.conv3x3_to_k(sd[name + ".weight"], c_pad)
-            W[name] = self._pw([wk], sd[name + ".bias"], conv_tiles(lvl), 9, wk.shape[1] // 9)
+            W[name] = self._pw([wk], sd[name + ".bias"], conv_tiles(lvl if tiles_lvl is None else tiles_lvl), 9, wk.shape[1] // 9)
 
         def resnet(r: ResnetDesc, lvl):
             conv3(r.name + ".conv1", lvl)
@@ -245,7 +245,7 @@ class UNetEngine:
                 if s.tfm:
                     tfm(s.tfm, i); lvl_of[s.tfm.name] = i
             if g.downsamplers[i]:
-                conv3(g.downsamplers[i], i)      # computed at the input resolution, even pixels kept
+                conv3(g.downsamplers[i], i, tiles_lvl=i + 1)    # stride 2: its tiles are output pixels (strided TMA boxes)
         top = len(g.down) - 1
         resnet(g.mid[0], top); tfm(g.mid[1], top); resnet(g.mid[2], top)
         lvl_of[g.mid[0].name] = lvl_of[g.mid[1].name] = lvl_of[g.mid[2].name] = top

@@ -26,7 +26,7 @@ from audioldm_with_lora_b200 import _lib, ops, packing  # noqa: E402
 
 NAMES = {0: "entry", 1: "prologue done", 2: "pdl_wait done", 3: "producer: 1st TMA issued", 4: "producer: stages filled",
          5: "producer: done", 6: "mma: 1st full", 7: "mma: 2nd full", 8: "mma: kb 17", 9: "mma: last full", 10: "mma: tfull commit",
-         16: "epi c0: math done", 17: "epi c0: staging free", 18: "epi c0: smem written", 19: "epi c0: store issued",
+         16: "epi c0: math done", 17: "epi c0: 1st tmem_ld back", 18: "epi c0: smem written", 19: "epi c0: store issued",
          20: "epi c2: math done", 21: "epi c2: staging free", 22: "epi c2: smem written", 23: "epi c2: store issued",
          12: "epi: tfull seen", 13: "epi: tile done", 14: "epi: stores complete", 15: "exit"}
 g = torch.Generator().manual_seed(0)

@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_train.py -q -m gpu -x > gpurun_out/r02_tests26.log 2>&1; tail -5 gpurun_out/r02_tests26.log
+run() { echo "== $*"; env "$@" timeout 300 python tools/step_time.py 1 2>&1 | tail -1; }
+{
+run B200LDM_LIB=audioldm_with_lora_b200/variants/libb200ldm_prev.so
+run A=new
+} > gpurun_out/r02_exp26.log 2>&1
+cat gpurun_out/r02_exp26.log
