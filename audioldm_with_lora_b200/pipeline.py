@@ -102,6 +102,7 @@ class AudioLDMPipeline:
         self.branches = int(os.environ.get("B200_BRANCHES", "1")) if branches is None else int(branches)
         self._loops: Dict[tuple, _LoopState] = {}
         self._tail_graphs: Dict[tuple, Optional[tuple]] = {}
+        self.tail_launches = 0
         # VAE decoder: a torch module with diffusers key names is re-hosted on the sm_100a kernels (vae.B200VaeDecoder,
         # SURVEY 8(f) item 1) unless b200_vae=False / B200_VAE=0 keeps it on the torch-eager reference path.
         if b200_vae is None:
@@ -312,8 +313,11 @@ class AudioLDMPipeline:
                         self.vocoder(self.decode_latents(z).squeeze(1).to(self.tail_dtype))
                 torch.cuda.current_stream().wait_stream(s)
                 g = torch.cuda.CUDAGraph()
+                from . import _lib
+                n0 = _lib.launch_count
                 with torch.cuda.graph(g), torch.no_grad():
                     out = self.vocoder(self.decode_latents(z).squeeze(1).to(self.tail_dtype))
+                self.tail_launches = _lib.launch_count - n0        # sm_100a kernel launches captured into the tail graph
                 ent = self._tail_graphs[key] = (g, z, out)
             except Exception:                           # noqa: BLE001 -- the tail is not the B200 path: eager is equivalent
                 torch.cuda.synchronize()

@@ -7,9 +7,10 @@
 Workload (BASELINE.json configs[1]): AudioLDM-S architecture (random-init, seed 0) + rank-8 LoRA on
 attn q/k/v/out, batch 8 prompts per GPU, 200 DDIM steps, CFG 2.5, 10 s clips, bf16 kernels with fp32
 accumulation, synthetic L2-normalised CLAP embeddings.  One bench "step" = one batch of 8 clips
-through the whole path (200 x {CFG-doubled UNet, guidance, DDIM update} + VAE decode + vocoder).
+through the whole path (200 x {CFG-doubled UNet, guidance, DDIM update} + VAE decode + HiFi-GAN vocoder, all of it on the
+hand-written sm_100a kernels).
 
-  value  : B*10 s*K / device time, inputs already resident in HBM (denoise loop + the torch VAE/vocoder tail, both replayed from CUDA graphs)
+  value  : B*10 s*K / device time, inputs already resident in HBM (denoise loop + the VAE / vocoder tail, both replayed from CUDA graphs)
   e2e    : the same through the public call `AudioLDMPipeline.__call__(prompt_embeds=<host tensors>, ...)`
            returning host numpy audio (H2D of embeddings/latents and D2H of waveforms inside the timing)
   roofline: the implicit-GEMM kernel (all conv / linear layers, ~89 % of the step's FLOPs) timed per
@@ -487,6 +488,7 @@ def main():
         tail_ms = e0.elapsed_time(e1)
         by, launches_per_step = (profile_kernels(pipe, lat_d, pos_d, neg_d) if rank == 0 else ({}, 0))
 
+    pipe_vae, pipe_voc, tail_launches = type(pipe.vae).__name__, type(pipe.vocoder).__name__, pipe.tail_launches
     clips = BATCH * world * args.steps
     value = clips * CLIP_S / (ms_res / 1e3)
     e2e_value = clips * CLIP_S / e2e_s
@@ -527,10 +529,12 @@ def main():
         "unet_step_ms": unet_step_ms,
         "unet_step_tflops": unet_flops / (unet_step_ms / 1e3) / 1e12,
         "tail_ms_per_batch": tail_ms,
+        "tail": {"vae_decoder": pipe_vae, "vocoder": pipe_voc, "launches_per_batch": int(tail_launches),
+                 "note": "B200VaeDecoder / B200HifiGan = the same sm_100a kernels as the UNet (SURVEY 8f items 1-2); torch modules = reference path"},
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": int(pos_h.numel() * 4 + neg_h.numel() * 4 + lat_h.numel() * 4),
                 "d2h_bytes_per_step": int(audio.nbytes)},
-        "gpu_launches": int(launches_per_step * STEPS_DDIM * args.steps),
+        "gpu_launches": int((launches_per_step * STEPS_DDIM + tail_launches) * args.steps),
         "launches_per_denoise_step": int(launches_per_step),
         "clocks": sampler.result(),
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: all conv/linear layers)",
