@@ -149,9 +149,17 @@ __device__ long long s_tl[48];
 
 template <int D, int KV>
 __global__ void __launch_bounds__(kAttnThreads)
-attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
+attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV,
+                 const __grid_constant__ CUtensorMap tmKs, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Q and K (the K-major operands of S = Q K^T) as whole rows of D * 2 bytes in the 64- / 128-byte swizzled layout when a
+  // row IS a swizzle span (head_dim 32 / 64): one TMA piece per row instead of D / 8 (the copy engine moves about one
+  // piece per clock per SM, and the key blocks were waiting for it: profiles/r02_attn_timeline.md).  V stays in the
+  // 16-byte core-matrix layout (it is the MN-major operand of P V).
+  constexpr bool kSwz = (D == 32 || D == 64);
+  constexpr uint64_t kSwzMode = D == 64 ? SWZ_128B : SWZ_64B;
+  constexpr uint32_t kSwzSbo = 8 * D * 2;       // 8 rows of D * 2 bytes
   constexpr int kKV = KV;
   constexpr int kTileBytes = 128 * D * 2;       // the Q tile
   constexpr int kKVTile = KV * D * 2;           // one K / V tile
@@ -186,6 +194,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmKV);
+    if (kSwz) tma_prefetch_desc(&tmKs);
     mbar_init(q_full, 1);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&kv_full[i], 1);
@@ -225,7 +235,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     {
       if (elect_one()) {
         mbar_expect_tx(q_full, kTileBytes);
-        tma_load_4d(sQ, &tmQKV, q_full, 0, q0, chunk_q, b);
+        if (kSwz) tma_load_3d(sQ, &tmQKV, q_full, h * D, q0, b);
+        else tma_load_4d(sQ, &tmQKV, q_full, 0, q0, chunk_q, b);
       }
       int s = 0;
       uint32_t ph = 0;
@@ -234,7 +245,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         uint8_t* k_dst = sKV + s * kStageBytes;
         if (elect_one()) {
           mbar_expect_tx(&kv_full[s], 2 * kKVTile);
-          tma_load_4d(k_dst, &tmKV, &kv_full[s], 0, j * kKV, chunk_k, b);
+          if (kSwz) tma_load_3d(k_dst, &tmKs, &kv_full[s], p.heads * D + h * D, j * kKV, b);
+          else tma_load_4d(k_dst, &tmKV, &kv_full[s], 0, j * kKV, chunk_k, b);
           tma_load_4d(k_dst + kKVTile, &tmKV, &kv_full[s], 0, j * kKV, chunk_v, b);
         }
         if (++s == p.stages) {
@@ -269,8 +281,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < D / 16; ++k) {
-            const uint64_t a_desc = make_smem_desc(q_addr + k * 4096, q_lbo, q_sbo, SWZ_NONE);
-            const uint64_t b_desc = make_smem_desc(k_addr + k * 2 * kChunk, k_lbo, k_sbo, SWZ_NONE);
+            // swizzled rows: a 16-element K step is +32 bytes inside the swizzle span (as in conv_gemm.cu)
+            const uint64_t a_desc = kSwz ? make_smem_desc(q_addr + k * 32, 16, kSwzSbo, kSwzMode)
+                                         : make_smem_desc(q_addr + k * 4096, q_lbo, q_sbo, SWZ_NONE);
+            const uint64_t b_desc = kSwz ? make_smem_desc(k_addr + k * 32, 16, kSwzSbo, kSwzMode)
+                                         : make_smem_desc(k_addr + k * 2 * kChunk, k_lbo, k_sbo, SWZ_NONE);
             umma_bf16_ss(t_s, a_desc, b_desc, idesc_s, k != 0);
           }
           umma_commit(s_full);
@@ -396,10 +411,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 }
 
 template <int D, int KV>
-static int launch_attention(const CUtensorMap& tm, const CUtensorMap& tmkv, AttnParams& p, cudaStream_t stream) {
+static int launch_attention(const CUtensorMap& tm_pieces, const CUtensorMap& tmkv, const void* qkv, AttnParams& p, cudaStream_t stream) {
   constexpr int kTileBytes = 128 * D * 2;
   constexpr int kStageBytes = 2 * KV * D * 2 + 2 * KV * 16;
-  const int fixed = kTileBytes + kQ * KV * 2 + 128 /*barriers*/ + 128 /*align*/;
+  const int fixed = kTileBytes + kQ * KV * 2 + 128 /*barriers*/ + 1024 /*align*/;
   // resident CTAs per SM are set by TMEM: 512 / tmem_cols (4, 2 or 1); give each its share of shared memory.  The K/V
   // ring wants >= 2 stages: with one, the next block's loads start only after the current block's P V has completed (the
   // CTA timeline showed exactly that at head_dim 48: profiles/r02_attn_timeline.md), so a fourth co-resident CTA is given
@@ -422,9 +437,22 @@ static int launch_attention(const CUtensorMap& tm, const CUtensorMap& tmkv, Attn
     if (e != cudaSuccess) return fail(B200_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
+  // head_dim 32 / 64: Q and K tiles as whole rows (rank-3 maps over [3C, seq, batch], 64- / 128-byte swizzle)
+  CUtensorMap tm = tm_pieces, tmks = tmkv;
+  if (D == 32 || D == 64) {
+    const uint64_t C3 = static_cast<uint64_t>(3) * p.heads * D;
+    uint64_t dims[3] = {C3, (uint64_t)p.seq, (uint64_t)p.batch};
+    uint64_t strides[2] = {C3, (uint64_t)p.seq * C3};
+    const CUtensorMapSwizzle swz = D == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    uint32_t box_q[3] = {(uint32_t)D, 128, 1}, box_k[3] = {(uint32_t)D, (uint32_t)KV, 1};
+    int rc = make_tmap_bf16(&tm, qkv, 3, dims, strides, box_q, swz);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmks, qkv, 3, dims, strides, box_k, swz);
+    if (rc) return rc;
+  }
   dim3 grid((p.seq + kQ - 1) / kQ, p.batch * p.heads);
   B200_CHECK_PDL("attention", launch_pdl(attention_kernel<D, KV>, grid, dim3(kAttnThreads), (size_t)smem_bytes, stream, 0, tm,
-                                         tmkv, p));
+                                         tmkv, tmks, p));
   return B200_OK;
 }
 
@@ -477,12 +505,12 @@ static int attention_impl(const void* qkv, void* out, float* lse, int batch, int
     if (rc) return rc;
   }
   switch (head_dim) {
-    case 32: return kv == 64 ? launch_attention<32, 64>(tm, tmkv, p, stream) : launch_attention<32, 128>(tm, tmkv, p, stream);
-    case 48: return kv == 64 ? launch_attention<48, 64>(tm, tmkv, p, stream) : launch_attention<48, 128>(tm, tmkv, p, stream);
-    case 64: return launch_attention<64, 128>(tm, tmkv, p, stream);
-    case 80: return launch_attention<80, 128>(tm, tmkv, p, stream);
-    case 96: return launch_attention<96, 128>(tm, tmkv, p, stream);
-    case 160: return launch_attention<160, 128>(tm, tmkv, p, stream);
+    case 32: return kv == 64 ? launch_attention<32, 64>(tm, tmkv, qkv, p, stream) : launch_attention<32, 128>(tm, tmkv, qkv, p, stream);
+    case 48: return kv == 64 ? launch_attention<48, 64>(tm, tmkv, qkv, p, stream) : launch_attention<48, 128>(tm, tmkv, qkv, p, stream);
+    case 64: return launch_attention<64, 128>(tm, tmkv, qkv, p, stream);
+    case 80: return launch_attention<80, 128>(tm, tmkv, qkv, p, stream);
+    case 96: return launch_attention<96, 128>(tm, tmkv, qkv, p, stream);
+    case 160: return launch_attention<160, 128>(tm, tmkv, qkv, p, stream);
     default: return fail(B200_ERR_UNSUPPORTED, "attention: head_dim %d unsupported (32/48/64/80/96/160)", head_dim);
   }
 }
