@@ -174,12 +174,15 @@ class UNetEngine:
             max_bn: int = 256) -> PackedWeight:
         n = segs[0].shape[0]
         num_kb = (ntaps * c0 + c1 + c2) // 64
+        pair = None
         if block_n:
             bn, ks = block_n, 1
         else:
-            bn, ks = ops.choose_tiling(n, m_tiles, num_kb, geglu, allow_split=split,
-                                       num_sms=getattr(self, "_tiling_sms", ops.NUM_SMS), max_bn=max_bn)
-        return packing.pack(segs, bias, bn, ntaps, c0, c1, c2, geglu, device=self.device, ksplit=ks)
+            bn, ks, pair = ops.choose_tiling_ex(n, m_tiles, num_kb, geglu, allow_split=split,
+                                                num_sms=getattr(self, "_tiling_sms", ops.NUM_SMS), max_bn=max_bn)
+        pw = packing.pack(segs, bias, bn, ntaps, c0, c1, c2, geglu, device=self.device, ksplit=ks)
+        pw.pair = pair
+        return pw
 
     def _ln_pack(self, w: Tensor, bias: Optional[Tensor], gamma: Tensor, beta: Tensor, m_tiles: int, c: int, *,
                  geglu: bool = False, lora_seg: Optional[Tensor] = None, max_bn: int = 256) -> PackedWeight:

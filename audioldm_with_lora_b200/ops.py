@@ -39,6 +39,7 @@ class PackedWeight:
     geglu: bool = False
     ksplit: int = 1               # > 1: split-K over this many CTAs per tile (small-M, long-K layers)
     alg_macs_per_row: Optional[float] = None   # algorithmic (unpadded) N*K of the layer; default: stored N*K
+    pair: Optional[bool] = None   # 2-CTA tiles for this layer (None: the global switch decides)
 
     @property
     def macs_per_row(self) -> float:
@@ -96,10 +97,68 @@ def _kb_cycles(bn: int, pair: bool = False) -> float:
     return max(2.0 * bn, (16384 + bn * (64 if pair else 128)) / TMA_BYTES_PER_CLK)
 
 
+# Measured per-launch model of conv_gemm_kernel (B200, isolated L2-warm replays of level-0 / level-1 / level-2 layer shapes,
+# gpurun_out/r02_conv_ab.log): time = tiles per CTA x k-blocks x KB_CLK + FIXED_CLK, in SM cycles.  The fixed part is
+# prologue + first operand fill + the LAST tile's epilogue (all of it exposed) + store drain + exit; 2-CTA tiles stream
+# operands a little faster per tile and pay ~4 k cycles more per launch (cluster syncs, pair tail).
+_KB_CLK = {(64, False): 300.0, (128, False): 350.0, (192, False): 480.0, (256, False): 620.0, (128, True): 325.0, (256, True): 620.0}
+_FIXED_CLK = {(64, False): 8600.0, (128, False): 10000.0, (192, False): 12200.0, (256, False): 14400.0, (128, True): 13900.0,
+              (256, True): 16700.0}
+_GEGLU_EPI_CLK = 6100.0          # GEGLU epilogue per tile (erf-GELU per gate): it, not the k-loop, paces short-K tiles
+TILING_MODEL = os.environ.get("B200_TILING_MODEL", "1")      # "1": the analytic model (pairs by global switch) -- measured best IN THE
+                                                             # STEP (4.17 vs 4.19 ms); "2": the table fitted to isolated replays below
+
+
+def choose_tiling_ex(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_split: bool = True,
+                     num_sms: int = NUM_SMS, max_bn: int = 256) -> Tuple[int, int, Optional[bool]]:
+    """(block_n, ksplit, pair) minimising the measured per-launch model on `num_sms` SMs; pair None = leave the 2-CTA
+    decision to the global switch (model 1).  Split-K only when it wins by > 25 %."""
+    bn1, ks1 = _choose_tiling_v1(n, m_tiles, num_kb, geglu, allow_split, num_sms, max_bn)
+    if TILING_MODEL == "1":
+        return bn1, ks1, None
+    if geglu or ks1 > 1:
+        # GEGLU tiles are paced by their epilogue and split-K layers by the reduce launch: not what the table below was
+        # measured on; the analytic choice stands there (measured in the step: DESIGN.md section 8)
+        return bn1, ks1, None
+    step = 128 if geglu else 64
+    best = {}
+    for ks in (1, 2, 3, 4):
+        if ks > 1 and (not allow_split or geglu or num_kb < 16 * ks // 2):
+            continue
+        for bn in range(step, max_bn + 1, step):
+            for pair in (False, True):
+                if pair and not (CTA_PAIR and bn % 128 == 0 and m_tiles >= 2 and ks == 1):
+                    continue
+                n_tiles = math.ceil(n / bn)
+                if pair:
+                    tpc = math.ceil(math.ceil(m_tiles / 2) * n_tiles / max(1, num_sms // 2))
+                else:
+                    tiles1 = m_tiles * n_tiles
+                    if ks > 1 and tiles1 > num_sms // 2:
+                        continue
+                    tpc = math.ceil(tiles1 * ks / num_sms)
+                per_tile = math.ceil(num_kb / ks) * _KB_CLK[(bn, pair)]
+                if geglu:
+                    per_tile = max(per_tile, _GEGLU_EPI_CLK)
+                cost = tpc * per_tile + _FIXED_CLK[(bn, pair)] + (7000 if ks > 1 else 0)
+                cost *= 1.0 + 0.02 * (n_tiles * bn - n) / max(n, 1)          # padded columns are wasted stores
+                key = 1 if ks == 1 else 2
+                if key not in best or cost < best[key][0] - 1e-9:
+                    best[key] = (cost, bn, ks, pair)
+    if 2 in best and best[2][0] < 0.75 * best[1][0]:
+        return best[2][1], best[2][2], False
+    return best[1][1], 1, best[1][3]
+
+
 def choose_tiling(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_split: bool = True,
                   num_sms: int = NUM_SMS, max_bn: int = 256) -> Tuple[int, int]:
-    """(block_n, ksplit) minimising a wave/cycle model on `num_sms` SMs (148, or this chain's share of them when
-    several sub-batch chains run concurrently); split-K only when it wins by > 25 %."""
+    """(block_n, ksplit) of choose_tiling_ex."""
+    return choose_tiling_ex(n, m_tiles, num_kb, geglu, allow_split, num_sms, max_bn)[:2]
+
+
+def _choose_tiling_v1(n: int, m_tiles: int, num_kb: int, geglu: bool = False, allow_split: bool = True,
+                      num_sms: int = NUM_SMS, max_bn: int = 256) -> Tuple[int, int]:
+    """Round-1 analytic model: a wave/cycle model with the per-SM ingest rate; split-K only when it wins by > 25 %."""
     step = 128 if geglu else 64
     best = {}
     for ks in (1, 2, 3, 4):
@@ -149,6 +208,8 @@ def conv_gemm(pw: PackedWeight, a0: Tensor, nb: int, h: int, w: int, out: Tensor
         m_out = nb * h * w if stride == 1 else nb * ((h - 1) // 2 + 1) * ((w - 1) // 2 + 1)
         info = {"flops": 2.0 * m_out * pw.macs_per_row, "m": nb * h * w, "n": pw.n_valid,
                 "k": pw.k, "bn": pw.block_n, "taps": pw.ntaps, "desc": f"ks{ksplit}" if ksplit > 1 else None}
+    if cta_pair is None and pw.pair is not None:
+        cta_pair = pw.pair
     pair = (int(CTA_PAIR and pw.block_n >= PAIR_MIN_BN) if cta_pair is None else (2 if cta_pair else 0))
     if gn_stat is not None:
         assert stride == 1 and not out_fp32 and ksplit == 1 and not pw.geglu and gn_stat.dtype == torch.float32
