@@ -11,7 +11,7 @@ from .model import (Attention, B200AttnProcessor, LoraLinear, UNet2DConditionMod
                     get_peft_model, get_peft_model_state_dict)
 from .pipeline import AudioLDMPipeline, AudioPipelineOutput
 from .scheduler import DDIMScheduler, PNDMScheduler
-from .vae import B200VaeDecoder
+from .vae import B200VaeDecoder, B200VaeEncoder
 from .vocoder import B200HifiGan
 
 __all__ = [
@@ -19,5 +19,5 @@ __all__ = [
     "parse_lora_state_dict", "to_peft_state_dict", "save_lora_checkpoint", "load_lora_checkpoint",
     "merge_lora_into_state_dict", "Attention", "B200AttnProcessor", "LoraLinear",
     "UNet2DConditionModel", "UNet2DConditionOutput", "get_peft_model", "get_peft_model_state_dict",
-    "AudioLDMPipeline", "AudioPipelineOutput", "DDIMScheduler", "PNDMScheduler", "B200VaeDecoder", "B200HifiGan",
+    "AudioLDMPipeline", "AudioPipelineOutput", "DDIMScheduler", "PNDMScheduler", "B200VaeDecoder", "B200VaeEncoder", "B200HifiGan",
 ]

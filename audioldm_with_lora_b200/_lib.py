@@ -41,6 +41,8 @@ _PROTOS = {
     "b200_gemm_nt": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200_conv1d": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
                             c_int, c_float, c_void_p, c_int, c_long, c_int, c_float, c_int, c_int, c_int, c_void_p]),
+    "b200_conv3x3_s2_pad01": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                      c_int, c_void_p]),
     "b200_lrelu_mean3": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_void_p, c_void_p]),
     "b200_f32_to_bf16": (c_int, [c_void_p, c_long, c_void_p, c_void_p]),
     "b200_groupnorm_apply": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,

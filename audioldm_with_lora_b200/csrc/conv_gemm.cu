@@ -982,7 +982,7 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
                           int ksplit, float* workspace, int cta_pair, const void* lora_down, int lora_rows, void* t_out,
                           const float* ln_g, const float* ln_ga, const float* ln_ba, float ln_eps, const float* ln_stats,
                           float* stat_out, void* stream_v, float* gn_stat = nullptr, int b_dynamic = 0,
-                          const struct Conv1dOpts* c1d = nullptr);
+                          const struct Conv1dOpts* c1d = nullptr, int s2_pad01 = 0);
 
 // 1-D tap walk and output geometry of b200_conv1d (everything else is the 2-D kernel with W = 1)
 struct Conv1dOpts {
@@ -1003,6 +1003,17 @@ extern "C" int b200_conv_gemm(const void* a0, int c0, const void* a1, int c1, co
   return conv_gemm_impl(a0, c0, a1, c1, a2, c2, nb, h, w, ntaps, stride, wpacked, n_pad, n_valid, bias, rowvec, rowvec_ld,
                         residual, res_ld, out, out_ld, out_fp32, geglu, block_n, max_ctas, ksplit, workspace, cta_pair,
                         nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, nullptr, stream_v);
+}
+
+// 3x3 stride-2 convolution with the VAE encoder's asymmetric padding (diffusers Downsample2D(padding=0):
+// F.pad(x, (0, 1, 0, 1)) then Conv2d(k 3, s 2, p 0)): out[ho, wo] = sum in[2 ho + kh, 2 wo + kw] W[kh, kw], zeros past the
+// bottom / right edge.  Same strided-TMA implicit GEMM as b200_conv_gemm(stride = 2); see include/b200ldm.h.
+extern "C" int b200_conv3x3_s2_pad01(const void* x, int c, int nb, int h, int w, const void* wpacked, int n_pad, int n_valid,
+                                     const float* bias, void* out, int out_ld, int block_n, int cta_pair, void* stream_v) {
+  B200_CHECK_ARG(h >= 2 && w >= 2, "conv3x3_s2_pad01: needs at least 2 x 2 pixels");
+  return conv_gemm_impl(x, c, nullptr, 0, nullptr, 0, nb, h, w, 9, 2, wpacked, n_pad, n_valid, bias, nullptr, 0, nullptr, 0, out,
+                        out_ld, 0, 0, block_n, 0, 1, nullptr, cta_pair, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr,
+                        nullptr, stream_v, nullptr, 0, nullptr, 1);
 }
 
 // b200_conv_gemm whose epilogue also leaves the partial GroupNorm statistics of its (bf16, stride-1, un-split) output for
@@ -1108,11 +1119,12 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
                           void* out, int out_ld, int out_fp32, int geglu, int block_n, int max_ctas,
                           int ksplit, float* workspace, int cta_pair, const void* lora_down, int lora_rows, void* t_out,
                           const float* ln_g, const float* ln_ga, const float* ln_ba, float ln_eps, const float* ln_stats,
-                          float* stat_out, void* stream_v, float* gn_stat, int b_dynamic, const Conv1dOpts* c1d) {
+                          float* stat_out, void* stream_v, float* gn_stat, int b_dynamic, const Conv1dOpts* c1d, int s2_pad01) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const bool s2 = stride == 2;                      // Downsample2D: computed at OUTPUT resolution (strided activation boxes)
-  const int m_h = s2 ? (h - 1) / 2 + 1 : (c1d ? c1d->m_h : h);     // output rows per image
-  const int w_o = s2 ? (w - 1) / 2 + 1 : w;         // output width
+  // (s2_pad01: the VAE encoder's Downsample2D(padding=0) = F.pad(x, (0, 1, 0, 1)) + conv k3 s2: taps at offsets 0..2, not -1..1)
+  const int m_h = s2 ? (s2_pad01 ? (h - 2) / 2 + 1 : (h - 1) / 2 + 1) : (c1d ? c1d->m_h : h);     // output rows per image
+  const int w_o = s2 ? (s2_pad01 ? (w - 2) / 2 + 1 : (w - 1) / 2 + 1) : w;                        // output width
   const bool fused_lora = lora_down != nullptr;
   const bool fused_ln = ln_g != nullptr;
   if (fused_ln) {
@@ -1150,6 +1162,8 @@ static int conv_gemm_impl(const void* a0, int c0, const void* a1, int c1, const 
   if (c1d) {
     p.dh0 = c1d->dh0; p.dh_step = c1d->dh_step; p.dw0 = 0; p.dw_end = 1;
     p.act_slope = c1d->act_slope; p.res_neg_gain = c1d->res_neg_gain; p.act_tanh = c1d->act_tanh;
+  } else if (ntaps == 9 && s2 && s2_pad01) {
+    p.dh0 = 0; p.dw0 = 0; p.dw_end = 3; p.dh_step = 1;
   } else if (ntaps == 9) {
     p.dh0 = -1; p.dw0 = -1; p.dw_end = 2; p.dh_step = 1;
   } else {

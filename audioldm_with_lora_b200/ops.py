@@ -617,3 +617,17 @@ def f32_to_bf16(x: Tensor, y: Tensor) -> Tensor:
     assert x.numel() == y.numel()
     call("b200_f32_to_bf16", ptr(x), x.numel(), ptr(y), stream())
     return y
+
+
+def conv3x3_s2_pad01(pw: PackedWeight, x: Tensor, nb: int, h: int, w: int, out: Tensor, cta_pair: Optional[bool] = None) -> Tensor:
+    """Downsample2D(padding=0) of the VAE encoder: F.pad(x, (0, 1, 0, 1)) + conv k3 s2; see b200_conv3x3_s2_pad01."""
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() == nb * h * w * pw.c0 and pw.ntaps == 9
+    assert out.dtype == torch.bfloat16 and pw.c1 == 0 and pw.c2 == 0 and pw.ksplit == 1
+    ho, wo = (h - 2) // 2 + 1, (w - 2) // 2 + 1
+    assert out.numel() == nb * ho * wo * pw.n_valid
+    info = {"flops": 2.0 * nb * ho * wo * pw.macs_per_row, "m": nb * ho * wo, "n": pw.n_valid, "k": pw.k, "bn": pw.block_n, "taps": 9,
+            "desc": "s2pad01"} if _lib.PROFILE is not None else None
+    pair = (int(CTA_PAIR and pw.block_n >= PAIR_MIN_BN) if cta_pair is None else (2 if cta_pair else 0))
+    call("b200_conv3x3_s2_pad01", ptr(x), pw.c0, nb, h, w, ptr(pw.w), pw.n_pad, pw.n_valid, ptr(pw.bias), ptr(out), pw.n_valid,
+         pw.block_n, pair, stream(), info=info)
+    return out

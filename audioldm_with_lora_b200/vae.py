@@ -116,10 +116,14 @@ class B200VaeDecoder:
         wo8 = torch.zeros(8, wo.shape[1]); wo8[:1] = wo
         bo8 = torch.zeros(8); bo8[:1] = sd["decoder.conv_out.bias"]
         W["conv_out"] = self._pw([wo8], bo8, tiles(len(self.block_out) - 1), 9, wo.shape[1] // 9, block_n=32)
-        # mid-block attention
-        a = "decoder.mid_block.attentions.0"
-        c = top
-        t = h * w
+        plan = {"W": W, "sizes": sizes}
+        plan.update(self._pack_mid_attention(W, "decoder.mid_block.attentions.0", top, nb, h * w))
+        self._plans[key] = plan
+        return plan
+
+    def _pack_mid_attention(self, W: dict, a: str, c: int, nb: int, t: int) -> dict:
+        """Weights of the single-head mid-block attention over t tokens per image (see the module docstring)."""
+        sd = self.sd
         mt = math.ceil(nb * t / 128)
         W["attn.q"] = self._pw([sd[a + ".to_q.weight"]], sd[a + ".to_q.bias"], mt, 1, c)
         W["attn.k"] = self._pw([sd[a + ".to_k.weight"]], None, mt, 1, c)
@@ -127,12 +131,10 @@ class B200VaeDecoder:
         b_out = sd[a + ".to_out.0.bias"] + sd[a + ".to_out.0.weight"] @ sd[a + ".to_v.bias"]
         W["attn.out"] = self._pw([sd[a + ".to_out.0.weight"]], b_out, mt, 1, c)
         t_pad = (t + 63) // 64 * 64
-        plan = {"W": W, "sizes": sizes, "t": t, "t_pad": t_pad,
+        return {"t": t, "t_pad": t_pad,
                 "bn_s": ops.choose_tiling(t, math.ceil(t / 128), c // 64, allow_split=False)[0],
                 "bn_vt": ops.choose_tiling(t, math.ceil(c / 128), c // 64, allow_split=False)[0],
                 "bn_o": 256 if c % 256 == 0 else (128 if c % 128 == 0 else 64)}
-        self._plans[key] = plan
-        return plan
 
     def _buf(self, key: tuple, shape, dtype) -> Tensor:
         """Persistent zero-initialised device buffer (padding regions are never written, so they stay zero)."""
@@ -220,12 +222,12 @@ class B200VaeDecoder:
         ho, wo = sizes[-1]
         return out8.view(nb, ho, wo, 8)[..., 0].reshape(nb, 1, ho, wo).clone()
 
-    def _mid_attention(self, plan: dict, ar: Arena, x: Tensor, nb: int, c: int, gn) -> Tensor:
+    def _mid_attention(self, plan: dict, ar: Arena, x: Tensor, nb: int, c: int, gn, a: str = "decoder.mid_block.attentions.0",
+                       lvl: int = 0) -> Tensor:
         W, t, t_pad = plan["W"], plan["t"], plan["t_pad"]
         bf16 = torch.bfloat16
-        a = "decoder.mid_block.attentions.0"
         slack = 256                                            # rows a [n_pad, c] "weight" view may read past the last image
-        n = gn(x, c, 0, a + ".group_norm", False, rows_slack=slack)
+        n = gn(x, c, lvl, a + ".group_norm", False, rows_slack=slack)
         m = nb * t
         q = ar.alloc((m, c), bf16)
         k = ar.alloc((m + slack, c), bf16)
@@ -267,3 +269,177 @@ def from_torch_decoder(vae, device="cuda") -> B200VaeDecoder:
     if cfg is not None and hasattr(cfg, "scaling_factor"):
         dec.config.scaling_factor = cfg.scaling_factor
     return dec
+
+
+class DiagonalGaussian:
+    """`latent_dist` of `AutoencoderKL.encode` (diffusers DiagonalGaussianDistribution): mean / logvar [B, 8, H, 16] fp32."""
+
+    def __init__(self, mean: Tensor, logvar: Tensor):
+        self.mean, self.logvar = mean, logvar.clamp(-30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+
+    def sample(self, generator=None) -> Tensor:
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
+
+    def mode(self) -> Tensor:
+        return self.mean
+
+
+class EncoderOutput:
+    def __init__(self, latent_dist: DiagonalGaussian):
+        self.latent_dist = latent_dist
+
+
+class B200VaeEncoder(B200VaeDecoder):
+    """`AutoencoderKL.encode` of the AudioLDM VAE on the sm_100a kernels (the training
+    loop's `vae.encode(batch["log_mel_spec"]).latent_dist.sample() * scaling_factor`,
+    /root/reference/script/train/train_audioldm_lora.py:495-496): log-mel [B, 1, T, 64] -> posterior over latents
+    [B, 8, T/4, 16].  conv_in (1 -> 128; the mel bin rides in channel 0 of a 64-channel K block), three down blocks of two
+    ResNets (128, 256, 512 channels) with Downsample2D(padding=0) between them (`ops.conv3x3_s2_pad01`: F.pad (0,1,0,1) +
+    conv k3 s2 as strided TMA boxes), the mid block (ResNet, head_dim-512 attention as in the decoder, ResNet), GroupNorm +
+    SiLU, and conv_out with quant_conv FOLDED in exactly (a 1x1 convolution after a 3x3 one composes: W' = W_q W_out per
+    tap, b' = W_q b_out + b_q).  Same kernels / arena as the decoder."""
+
+    def __init__(self, state_dict: Dict[str, Tensor], device="cuda", block_out=(128, 256, 512), latent: int = 8,
+                 layers: int = 2, groups: int = 32, eps: float = 1e-6):
+        super().__init__(state_dict, device, block_out, latent, layers, groups, eps)
+
+    def _enc_res_names(self):
+        out, prev = [], self.block_out[0]
+        for i, c in enumerate(self.block_out):
+            for j in range(self.layers):
+                out.append((f"encoder.down_blocks.{i}.resnets.{j}", prev, c, i))
+                prev = c
+        top = self.block_out[-1]
+        lvl = len(self.block_out) - 1
+        out += [("encoder.mid_block.resnets.0", top, top, lvl), ("encoder.mid_block.resnets.1", top, top, lvl)]
+        return out
+
+    def _enc_plan(self, nb: int, h: int, w: int) -> dict:
+        key = ("enc", nb, h, w)
+        if key in self._plans:
+            return self._plans[key]
+        sd, W = self.sd, {}
+        nlev = len(self.block_out)
+        sizes = [(h, w)]
+        for _ in range(nlev - 1):
+            sizes.append(((sizes[-1][0] - 2) // 2 + 1, (sizes[-1][1] - 2) // 2 + 1))
+
+        def tiles(lvl):
+            return ops.num_m_tiles(nb, *sizes[lvl])
+
+        w_in = sd["encoder.conv_in.weight"]                                    # [128, 1, 3, 3]
+        W["conv_in"] = self._pw([packing.conv3x3_to_k(w_in, C_IN_PAD)], sd["encoder.conv_in.bias"], tiles(0), 9, C_IN_PAD)
+        for name, cin, cout, lvl in self._enc_res_names():
+            W[name + ".conv1"] = self._pw([packing.conv3x3_to_k(sd[name + ".conv1.weight"])], sd[name + ".conv1.bias"],
+                                         tiles(lvl), 9, cin)
+            w2 = packing.conv3x3_to_k(sd[name + ".conv2.weight"])
+            if cin != cout:
+                ws = sd[name + ".conv_shortcut.weight"][:, :, 0, 0]
+                W[name + ".conv2"] = self._pw([w2, ws], sd[name + ".conv2.bias"] + sd[name + ".conv_shortcut.bias"],
+                                             tiles(lvl), 9, cout, cin)
+            else:
+                W[name + ".conv2"] = self._pw([w2], sd[name + ".conv2.bias"], tiles(lvl), 9, cout)
+        for i in range(nlev - 1):
+            n = f"encoder.down_blocks.{i}.downsamplers.0.conv"
+            W[n] = self._pw([packing.conv3x3_to_k(sd[n + ".weight"])], sd[n + ".bias"], tiles(i + 1), 9, sd[n + ".weight"].shape[1],
+                            split=False)
+        # conv_out with quant_conv folded in: 2 * latent fp32 columns (mean | logvar)
+        w_out, b_out = sd["encoder.conv_out.weight"], sd["encoder.conv_out.bias"]
+        w_q, b_q = sd["quant_conv.weight"][:, :, 0, 0], sd["quant_conv.bias"]
+        fold = torch.einsum("oc,cikl->oikl", w_q, w_out)
+        W["conv_out"] = self._pw([packing.conv3x3_to_k(fold)], w_q @ b_out + b_q, tiles(nlev - 1), 9, w_out.shape[1], block_n=32)
+        plan = {"W": W, "sizes": sizes}
+        top = self.block_out[-1]
+        plan.update(self._pack_mid_attention(W, "encoder.mid_block.attentions.0", top, nb, sizes[-1][0] * sizes[-1][1]))
+        self._plans[key] = plan
+        return plan
+
+    def _pw(self, segs, bias, m_tiles, ntaps, c0, c1=0, block_n=None, split=True):
+        return super()._pw(segs, bias, m_tiles, ntaps, c0, c1, block_n)
+
+    @torch.no_grad()
+    def encode(self, mel: Tensor) -> EncoderOutput:
+        """mel [B, 1, T, 64] (any float dtype; T and 64 at least 4) -> EncoderOutput(latent_dist) like diffusers."""
+        nb, cm, h, w = mel.shape
+        if cm != 1:
+            raise ValueError(f"expected a 1-channel log-mel spectrogram, got {cm} channels")
+        # (no CPU fallback: ops -> _lib.ptr() refuses CPU tensors)
+        plan = self._enc_plan(nb, h, w)
+        W, sizes, S = plan["W"], plan["sizes"], self._small
+        nlev = len(self.block_out)
+        need = nb * h * w * self.block_out[0] * 2 * 5 + (128 << 20)
+        if self.arena is None or self.arena.buf.numel() < need:
+            self.arena = Arena(need, self.device)
+        ar = self.arena
+        bf16 = torch.bfloat16
+
+        def M(lvl):
+            return nb * sizes[lvl][0] * sizes[lvl][1]
+
+        def gn(x, c, lvl, name, silu, rows_slack=0):
+            hh, ww = sizes[lvl]
+            y = ar.alloc((M(lvl) + rows_slack, c), bf16)
+            ops.groupnorm_silu(x, c, None, 0, nb, hh * ww, S[name + ".weight"], S[name + ".bias"], self.eps, silu, y, self.groups)
+            return y
+
+        def conv(name, a0, lvl, *, a1=None, residual=None, out=None):
+            pw = W[name]
+            hh, ww = sizes[lvl]
+            if out is None:
+                out = ar.alloc((M(lvl), pw.n_valid), bf16)
+            ops.conv_gemm(pw, a0, nb, hh, ww, out, a1=a1, residual=residual)
+            return out
+
+        def resnet(name, x, cin, cout, lvl):
+            n1 = gn(x, cin, lvl, name + ".norm1", True)
+            h1 = conv(name + ".conv1", n1, lvl)
+            ar.release(n1)
+            n2 = gn(h1, cout, lvl, name + ".norm2", True)
+            ar.release(h1)
+            out = conv(name + ".conv2", n2, lvl, a1=x) if cin != cout else conv(name + ".conv2", n2, lvl, residual=x)
+            ar.release(n2)
+            ar.release(x)
+            return out
+
+        xin = self._buf(("enc_xin", nb, h, w), (nb, h * w, C_IN_PAD), bf16)
+        xin[:, :, 0].copy_(mel.reshape(nb, h * w))
+        x = conv("conv_in", xin, 0)
+        prev = self.block_out[0]
+        for i, c in enumerate(self.block_out):
+            for j in range(self.layers):
+                x = resnet(f"encoder.down_blocks.{i}.resnets.{j}", x, prev, c, i)
+                prev = c
+            if i != nlev - 1:
+                hs, ws = sizes[i]
+                y = ar.alloc((M(i + 1), c), bf16)
+                ops.conv3x3_s2_pad01(W[f"encoder.down_blocks.{i}.downsamplers.0.conv"], x, nb, hs, ws, y)
+                ar.release(x)
+                x = y
+        top, lvl = self.block_out[-1], nlev - 1
+        x = resnet("encoder.mid_block.resnets.0", x, top, top, lvl)
+        x = self._mid_attention(plan, ar, x, nb, top, gn, a="encoder.mid_block.attentions.0", lvl=lvl)
+        x = resnet("encoder.mid_block.resnets.1", x, top, top, lvl)
+        n = gn(x, top, lvl, "encoder.conv_norm_out", True)
+        ar.release(x)
+        mom = self._buf(("enc_mom", nb, h, w), (M(lvl), 2 * self.latent), torch.float32)
+        conv("conv_out", n, lvl, out=mom)
+        ar.release(n)
+        assert not ar.live, f"arena leak: {len(ar.live)} buffers"
+        ho, wo = sizes[-1]
+        m4 = mom.view(nb, ho, wo, 2 * self.latent).permute(0, 3, 1, 2)
+        return EncoderOutput(DiagonalGaussian(m4[:, : self.latent].contiguous(), m4[:, self.latent:].contiguous()))
+
+
+def from_torch_encoder(vae, device="cuda") -> B200VaeEncoder:
+    """Build the B200 encoder from a module / state dict with diffusers key names (`encoder.*`, `quant_conv.*`)."""
+    sd = vae if isinstance(vae, dict) else vae.state_dict()
+    sd = {k: v for k, v in sd.items() if k.startswith(("encoder.", "quant_conv."))}
+    cfg = getattr(vae, "config", None)
+    block_out = tuple(getattr(cfg, "block_out_channels", (128, 256, 512)))
+    enc = B200VaeEncoder(sd, device=device, block_out=block_out)
+    if cfg is not None and hasattr(cfg, "scaling_factor"):
+        enc.config.scaling_factor = cfg.scaling_factor
+    return enc

@@ -78,6 +78,13 @@ int b200_gn_stat_slabs(int nb, int h, int w);
 int b200_gemm_nt(const void* a, int m, int k, const void* b, int b_rows, int n_valid, void* out, int out_ld, int out_fp32,
                  int block_n, int cta_pair, void* stream);
 
+/* 3x3 stride-2 convolution with asymmetric padding -- diffusers Downsample2D(padding=0) of the VAE ENCODER
+ * (`vae.encode(batch["log_mel_spec"])`, /root/reference/script/train/train_audioldm_lora.py:495): F.pad(x, (0, 1, 0, 1)) then
+ * Conv2d(k 3, s 2, p 0), i.e. out[ho, wo] = sum_{kh, kw} x[2 ho + kh, 2 wo + kw] W[kh, kw] with zeros past the bottom / right
+ * edge.  x bf16 NHWC [nb, h, w, c]; wpacked as for b200_conv_gemm (tap-major); out bf16 [nb, (h-2)/2+1, (w-2)/2+1, n_valid]. */
+int b200_conv3x3_s2_pad01(const void* x, int c, int nb, int h, int w, const void* wpacked, int n_pad, int n_valid,
+                          const float* bias, void* out, int out_ld, int block_n, int cta_pair, void* stream);
+
 /* 1-D convolution over time-major bf16 activations x [nb, len, c] -- the layers of the HiFi-GAN vocoder
  * (transformers SpeechT5HifiGan, loaded at train_audioldm_lora.py:371 and run at the end of AudioLDMPipeline.__call__:
  * /root/reference/app.py:14, generate_audio.py:47-52): nn.Conv1d with dilation, and -- one launch per output phase --

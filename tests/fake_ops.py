@@ -157,7 +157,7 @@ def groupnorm_silu(x0, c0, x1, c1, nb, hw, gamma, beta, eps, silu, y, groups=32)
     r = F.group_norm(x.permute(0, 2, 1), groups, gamma, beta, eps)
     if silu:
         r = F.silu(r)
-    y.view(nb, hw, c0 + c1).copy_(r.permute(0, 2, 1).to(bf16))
+    y.reshape(-1)[: nb * hw * (c0 + c1)].view(nb, hw, c0 + c1).copy_(r.permute(0, 2, 1).to(bf16))    # (y may carry slack rows)
     return y
 
 
@@ -426,7 +426,7 @@ def install(monkeypatch, ops_module):
     for name in ("conv_gemm", "groupnorm_silu", "layernorm", "attention", "time_class_embed",
                  "pack_nchw_to_nhwc", "unpack_nhwc_to_nchw", "upsample_nearest", "sampler_step", "add_noise",
                  "adamw_flat", "mse_partial", "set_sm_budget", "gn_stat_slabs", "groupnorm_apply", "linear_lora_ok", "linear_lora", "linear_ln", "linear_stats",
-                 "conv1d", "lrelu_mean3", "f32_to_bf16") + TRAIN_OPS:
+                 "conv1d", "lrelu_mean3", "f32_to_bf16", "gemm_nt", "softmax_rows", "conv3x3_s2_pad01") + TRAIN_OPS:
         monkeypatch.setattr(ops_module, name, globals()[name])
 
 
@@ -471,3 +471,29 @@ def lrelu_mean3(a0, a1, a2, in_slope, out_slope, y):
 def f32_to_bf16(x, y):
     y.copy_(x.to(y.dtype))
     return y
+
+
+# ------------------------------------------------------------------------------------------ VAE
+def gemm_nt(a, b, n_valid, out, block_n, out_ld=None):
+    acc = a.float() @ b[:n_valid].float().T
+    ld = out_ld if out_ld is not None else n_valid
+    o = torch.as_strided(out, (a.shape[0], n_valid), (ld, 1), out.storage_offset())
+    o.copy_(acc.to(out.dtype))
+    return out
+
+
+def softmax_rows(s, rows, cols, cols_pad, p, scale=1.0):
+    pr = F.softmax(s[:rows, :cols].float() * scale, dim=-1)
+    p[:rows, :cols_pad] = 0
+    p[:rows, :cols] = pr.to(p.dtype)
+    return p
+
+
+def conv3x3_s2_pad01(pw, x, nb, h, w, out, cta_pair=None):
+    """b200_conv3x3_s2_pad01 semantics: F.pad(x, (0, 1, 0, 1)) + conv k3 s2 p0 over NHWC bf16."""
+    c = pw.c0
+    xn = x.view(nb, h, w, c).float().permute(0, 3, 1, 2)
+    wt = pw.w.float().view(pw.n_pad, 3, 3, c).permute(0, 3, 1, 2)[:pw.n_valid]
+    y = F.conv2d(F.pad(xn, (0, 1, 0, 1)), wt, pw.bias[:pw.n_valid] if pw.bias is not None else None, stride=2)
+    out.view(nb, y.shape[2], y.shape[3], pw.n_valid).copy_(y.permute(0, 2, 3, 1).to(out.dtype))
+    return out

@@ -82,3 +82,51 @@ def test_pipeline_tail_with_b200_vae_matches_torch_tail():
     assert mel.logmel_l1(wa * gain, wb * gain) < 0.1
     wa2 = a.latents_to_waveform(lat).float().cpu()          # second call replays the captured tail graph
     assert torch.equal(wa, wa2)
+
+
+# ------------------------------------------------------------------------------------------ encoder
+@pytest.mark.parametrize("nb,h,w,c,co", [(2, 64, 64, 128, 128), (1, 37, 32, 256, 256), (3, 9, 16, 64, 128), (1, 1024, 64, 128, 128)])
+def test_conv3x3_s2_pad01_matches_torch(nb, h, w, c, co):
+    """Downsample2D(padding=0) of the VAE encoder: F.pad(x, (0, 1, 0, 1)) + conv k3 s2 p0, as strided TMA boxes."""
+    from audioldm_with_lora_b200 import ops, packing
+    g = torch.Generator().manual_seed(h * 7 + w)
+    x = torch.randn(nb, c, h, w, generator=g).to(torch.bfloat16)
+    wt = torch.randn(co, c, 3, 3, generator=g) / (9 * c) ** 0.5
+    b = torch.randn(co, generator=g) * 0.1
+    ho, wo = (h - 2) // 2 + 1, (w - 2) // 2 + 1
+    bn = ops.choose_tiling(co, ops.num_m_tiles(nb, ho, wo), 9 * c // 64, allow_split=False)[0]
+    pw = packing.pack([packing.conv3x3_to_k(wt)], b, bn, 9, c, device=DEV)
+    xin = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    out = torch.full((nb, ho, wo, co), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.conv3x3_s2_pad01(pw, xin, nb, h, w, out)
+    ref = F.conv2d(F.pad(x.float(), (0, 1, 0, 1)), wt.to(torch.bfloat16).float(), b, stride=2)
+    assert ref.shape == (nb, co, ho, wo) and torch.isfinite(out).all()
+    assert rel(out.permute(0, 3, 1, 2), ref) < 5e-3
+
+
+@pytest.fixture(scope="module")
+def enc_pair():
+    from audioldm_with_lora_b200 import synthetic
+    from audioldm_with_lora_b200.vae import from_torch_encoder
+    from oracle import vae_ref
+    sd = synthetic.random_state_dict_from_shapes(vae_ref.vae_encoder_param_shapes(), seed=11, std=0.05)
+    return sd, from_torch_encoder(sd, DEV)
+
+
+@pytest.mark.parametrize("nb,t", [(2, 64), (1, 1024), (3, 100)])
+def test_vae_encode_matches_oracle(enc_pair, nb, t):
+    """`vae.encode(log_mel).latent_dist` (train_audioldm_lora.py:495) on the kernels vs the fp32 oracle on the same weights."""
+    from oracle import vae_ref
+    sd, enc = enc_pair
+    g = torch.Generator().manual_seed(nb * 100 + t)
+    mel = (torch.randn(nb, 1, t, 64, generator=g) * 2.0 - 4.0)
+    dsd = {k: v.to(DEV) for k, v in sd.items()}
+    with torch.no_grad():
+        mean, logvar = vae_ref.vae_encode(dsd, mel.to(DEV))
+    d = enc.encode(mel.to(DEV)).latent_dist
+    assert d.mean.shape == mean.shape == (nb, 8, t // 4, 16) and d.mean.dtype == torch.float32
+    assert torch.isfinite(d.mean).all() and torch.isfinite(d.logvar).all()
+    assert rel(d.mean, mean) < TOL and rel(d.logvar, logvar) < TOL
+    assert torch.equal(d.mean, enc.encode(mel.to(DEV)).latent_dist.mean)          # deterministic
+    lat = d.sample(torch.Generator(device=DEV).manual_seed(3)) * enc.config.scaling_factor
+    assert lat.shape == mean.shape and torch.isfinite(lat).all()
