@@ -191,6 +191,23 @@ def timestep_embedding(t: Tensor, dim: int) -> Tensor:
     return torch.cat([emb[:, half:], emb[:, :half]], dim=-1)
 
 
+# Parity instrument (tests/test_gpu_train.py): with STORAGE_ROUND = torch.bfloat16 every tensor the B200 path keeps in HBM
+# between two kernels (conv / linear / norm / attention outputs) is rounded to that type here as well -- forward values
+# with a straight-through estimator, gradients through a hook -- while all arithmetic stays fp32.  The difference between
+# this and the plain fp32 run is what bf16 STORAGE costs; what remains against the kernels is arithmetic / bugs.
+STORAGE_ROUND = None
+
+
+def _st(x: Tensor) -> Tensor:
+    if STORAGE_ROUND is None:
+        return x
+    dt = STORAGE_ROUND
+    y = x + (x.to(dt).to(x.dtype) - x).detach()
+    if y.requires_grad:
+        y.register_hook(lambda g: g.to(dt).to(g.dtype))
+    return y
+
+
 def _gn(sd, name, x, groups, eps):
     return F.group_norm(x, groups, sd[name + ".weight"], sd[name + ".bias"], eps)
 
@@ -200,54 +217,54 @@ def _conv(sd, name, x, stride=1, padding=1):
 
 
 def _resnet(sd, name, x, emb, spec: UNetSpec):
-    h = F.silu(_gn(sd, name + ".norm1", x, spec.norm_num_groups, spec.norm_eps))
+    h = _st(F.silu(_gn(sd, name + ".norm1", x, spec.norm_num_groups, spec.norm_eps)))
     h = _conv(sd, name + ".conv1", h)
     t = F.linear(F.silu(emb), sd[name + ".time_emb_proj.weight"], sd[name + ".time_emb_proj.bias"])
-    h = h + t[:, :, None, None]
-    h = F.silu(_gn(sd, name + ".norm2", h, spec.norm_num_groups, spec.norm_eps))
+    h = _st(h + t[:, :, None, None])
+    h = _st(F.silu(_gn(sd, name + ".norm2", h, spec.norm_num_groups, spec.norm_eps)))
     h = _conv(sd, name + ".conv2", h)          # dropout p=0
     if name + ".conv_shortcut.weight" in sd:
         x = _conv(sd, name + ".conv_shortcut", x, padding=0)
-    return (x + h) / 1.0                        # output_scale_factor = 1
+    return _st((x + h) / 1.0)                   # output_scale_factor = 1
 
 
 def _attention(sd, name, x, heads: int, lora: LoraSet):
     """AttnProcessor2_0 with encoder_hidden_states=None (self-attention)."""
     B, S, C = x.shape
-    q = lora.linear(name + ".to_q", x, sd[name + ".to_q.weight"], None)
-    k = lora.linear(name + ".to_k", x, sd[name + ".to_k.weight"], None)
-    v = lora.linear(name + ".to_v", x, sd[name + ".to_v.weight"], None)
+    q = _st(lora.linear(name + ".to_q", x, sd[name + ".to_q.weight"], None))
+    k = _st(lora.linear(name + ".to_k", x, sd[name + ".to_k.weight"], None))
+    v = _st(lora.linear(name + ".to_v", x, sd[name + ".to_v.weight"], None))
     d = C // heads
     q = q.view(B, S, heads, d).transpose(1, 2)
     k = k.view(B, S, heads, d).transpose(1, 2)
     v = v.view(B, S, heads, d).transpose(1, 2)
     o = F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False)
-    o = o.transpose(1, 2).reshape(B, S, C)
+    o = _st(o.transpose(1, 2).reshape(B, S, C))
     return lora.linear(name + ".to_out.0", o, sd[name + ".to_out.0.weight"], sd[name + ".to_out.0.bias"])
 
 
 def _basic_transformer_block(sd, name, x, heads, lora):
     C = x.shape[-1]
-    ln = lambda n, y: F.layer_norm(y, (C,), sd[f"{name}.{n}.weight"], sd[f"{name}.{n}.bias"], 1e-5)
-    x = x + _attention(sd, name + ".attn1", ln("norm1", x), heads, lora)
-    x = x + _attention(sd, name + ".attn2", ln("norm2", x), heads, lora)   # encoder_hidden_states=None
-    h = F.linear(ln("norm3", x), sd[name + ".ff.net.0.proj.weight"], sd[name + ".ff.net.0.proj.bias"])
+    ln = lambda n, y: _st(F.layer_norm(y, (C,), sd[f"{name}.{n}.weight"], sd[f"{name}.{n}.bias"], 1e-5))
+    x = _st(x + _attention(sd, name + ".attn1", ln("norm1", x), heads, lora))
+    x = _st(x + _attention(sd, name + ".attn2", ln("norm2", x), heads, lora))   # encoder_hidden_states=None
+    h = _st(F.linear(ln("norm3", x), sd[name + ".ff.net.0.proj.weight"], sd[name + ".ff.net.0.proj.bias"]))
     val, gate = h.chunk(2, dim=-1)
-    h = val * F.gelu(gate)                       # GEGLU, exact erf gelu
+    h = _st(val * F.gelu(gate))                  # GEGLU, exact erf gelu
     h = F.linear(h, sd[name + ".ff.net.2.weight"], sd[name + ".ff.net.2.bias"])
-    return x + h
+    return _st(x + h)
 
 
 def _transformer2d(sd, name, x, spec: UNetSpec, lora):
     B, C, H, W = x.shape
     res = x
-    h = _gn(sd, name + ".norm", x, spec.norm_num_groups, 1e-6)
-    h = _conv(sd, name + ".proj_in", h, padding=0)
+    h = _st(_gn(sd, name + ".norm", x, spec.norm_num_groups, 1e-6))
+    h = _st(_conv(sd, name + ".proj_in", h, padding=0))
     h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
     h = _basic_transformer_block(sd, name + ".transformer_blocks.0", h, spec.num_heads, lora)
     h = h.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
     h = _conv(sd, name + ".proj_out", h, padding=0)
-    return h + res
+    return _st(h + res)
 
 
 def compute_emb(sd, spec: UNetSpec, timestep, class_labels: Tensor) -> Tensor:
@@ -272,7 +289,7 @@ def unet_forward(sd: Dict[str, Tensor], spec: UNetSpec, sample: Tensor, timestep
     lora = lora or LoraSet()
     boc = spec.block_out_channels
     emb = compute_emb(sd, spec, timestep, class_labels)
-    h = _conv(sd, "conv_in", sample)
+    h = _st(_conv(sd, "conv_in", sample))
     if taps is not None:
         taps["emb"] = emb; taps["conv_in"] = h
     skips = [h]
@@ -287,7 +304,7 @@ def unet_forward(sd: Dict[str, Tensor], spec: UNetSpec, sample: Tensor, timestep
                     taps[f"down_blocks.{i}.attentions.{j}"] = h
             skips.append(h)
         if i != len(boc) - 1:
-            h = _conv(sd, f"down_blocks.{i}.downsamplers.0.conv", h, stride=2, padding=1)
+            h = _st(_conv(sd, f"down_blocks.{i}.downsamplers.0.conv", h, stride=2, padding=1))
             skips.append(h)
     h = _resnet(sd, "mid_block.resnets.0", h, emb, spec)
     h = _transformer2d(sd, "mid_block.attentions.0", h, spec, lora)
@@ -307,6 +324,6 @@ def unet_forward(sd: Dict[str, Tensor], spec: UNetSpec, sample: Tensor, timestep
         if i != len(boc) - 1:
             size = skips[-1].shape[-2:]            # forward_upsample_size: explicit target size
             h = F.interpolate(h, size=tuple(size), mode="nearest")
-            h = _conv(sd, f"up_blocks.{i}.upsamplers.0.conv", h)
-    h = F.silu(_gn(sd, "conv_norm_out", h, spec.norm_num_groups, spec.norm_eps))
+            h = _st(_conv(sd, f"up_blocks.{i}.upsamplers.0.conv", h))
+    h = _st(F.silu(_gn(sd, "conv_norm_out", h, spec.norm_num_groups, spec.norm_eps)))
     return _conv(sd, "conv_out", h)

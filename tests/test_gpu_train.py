@@ -91,6 +91,50 @@ def test_loss_and_lora_grads_match_oracle(rank, targets, alpha, nb, h):
     assert worst < GRAD_TOL_ADAPTER, f"worst adapter-matrix error {worst:.3e}"
 
 
+def test_lora_grad_error_is_bf16_storage_not_arithmetic():
+    """Where the 4-5e-2 against fp32 autograd comes from.  The oracle re-run with every inter-kernel tensor (and the frozen
+    weights) ROUNDED TO BF16 -- values straight-through, gradients through hooks, all arithmetic still fp32
+    (oracle/unet_ref.py::STORAGE_ROUND) -- moves away from the plain fp32 oracle by as much as the kernels do (measured on
+    B200: 4.31e-2 for the rounding oracle, 4.37e-2 for the kernels, cosine 0.9992; the two differ from each other by 4.8e-2,
+    i.e. two realisations of the same rounding noise): the error budget is bf16 STORAGE of activations / gradients through
+    ~60 layers (what the reference's own `--mixed_precision bf16` runs incur), not the kernels' arithmetic.  Numbers go to
+    gpurun_out/train_parity_report.json."""
+    import json
+    from pathlib import Path
+    from oracle import unet_ref
+    unet, trainer, ref = _setup(8, ("to_q", "to_k", "to_v", "to_out.0"), None)
+    lat, noise, t, emb = _batch(2, 32)
+    ref.loss_and_grads(lat, noise, t, emb)
+    g_fp32 = _flat(ref, trainer, "grad").clone()
+    # the same oracle with bf16 storage: weights as the kernels hold them, activations / gradients rounded between "kernels"
+    sd_keep = ref.sd
+    ref.sd = {k: (v.to(torch.bfloat16).float() if v.dim() >= 2 else v) for k, v in sd_keep.items()}
+    unet_ref.STORAGE_ROUND = torch.bfloat16
+    try:
+        ref.loss_and_grads(lat, noise, t, emb)
+    finally:
+        unet_ref.STORAGE_ROUND = None
+        ref.sd = sd_keep
+    g_emul = _flat(ref, trainer, "grad").clone()
+    noisy = ref.noise_sched.add_noise(lat, noise, t)
+    trainer.flat_g.zero_()
+    trainer.forward_backward(noisy.to(DEV), t.to(DEV), emb.to(DEV), noise.to(DEV))
+    torch.cuda.synchronize()
+    g = trainer.flat_g.cpu()
+    rep = {"kernels_vs_fp32_oracle": rel(g, g_fp32), "kernels_vs_bf16_storage_oracle": rel(g, g_emul),
+           "bf16_storage_oracle_vs_fp32_oracle": rel(g_emul, g_fp32),
+           "cosine_kernels_fp32": torch.nn.functional.cosine_similarity(g, g_fp32, dim=0).item()}
+    out = Path(__file__).resolve().parents[1] / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / "train_parity_report.json").write_text(json.dumps(rep, indent=1))
+    print(rep)
+    assert rep["kernels_vs_fp32_oracle"] < GRAD_TOL
+    # storage rounding alone explains an error of the same size ...
+    assert rep["bf16_storage_oracle_vs_fp32_oracle"] > 0.4 * rep["kernels_vs_fp32_oracle"]
+    # ... and the kernels are no further from the fp32 truth than 2x what storage rounding alone costs
+    assert rep["kernels_vs_fp32_oracle"] < 2.0 * rep["bf16_storage_oracle_vs_fp32_oracle"] + 1e-2
+
+
 def test_train_steps_match_oracle_adamw():
     kw = dict(lr=1e-3, weight_decay=1e-2, num_training_steps=10)
     unet, trainer, ref = _setup(8, **kw)
