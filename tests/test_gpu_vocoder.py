@@ -100,9 +100,9 @@ def voc_pair():
     from audioldm_with_lora_b200 import tail
     from audioldm_with_lora_b200.vocoder import from_torch_vocoder
     voc = tail.build_vocoder(3)
-    with torch.no_grad():                 # random-init weights are tiny (std 0.01): scale up so every layer matters
+    with torch.no_grad():                 # random-init weights are tiny (std 0.01): scale up so every layer matters (x8 would saturate the final tanh)
         for p in voc.parameters():
-            p.mul_(8.0)
+            p.mul_(3.0)
     return voc.to(DEV), from_torch_vocoder(voc, DEV)
 
 
@@ -114,6 +114,7 @@ def test_b200_hifigan_matches_transformers(voc_pair, nb, t):
     with torch.no_grad():
         ref = voc(mel)
     got = mine(mel)
+    assert (ref.abs() > 0.999).float().mean() < 0.1, "reference output saturates the final tanh: the comparison would be vacuous"
     assert got.shape == ref.shape and got.dtype == torch.float32 and torch.isfinite(got).all()
     assert rel(got, ref) < TOL
     assert torch.equal(got, mine(mel))                       # deterministic

@@ -42,15 +42,16 @@ def test_transposed_conv_phase_decomposition_is_exact():
 @pytest.mark.parametrize("nb,t", [(2, 12), (1, 7)])
 def test_b200_hifigan_host_logic_matches_transformers(fake_kernels, nb, t):
     voc = tail.build_vocoder(3)
-    with torch.no_grad():                 # random-init weights are tiny (std 0.01): scale up so every layer matters
+    with torch.no_grad():                 # random-init weights are tiny (std 0.01): scale up so every layer matters (x8 would saturate the final tanh)
         for p in voc.parameters():
-            p.mul_(8.0)
+            p.mul_(3.0)
     mine = B200HifiGan(voc, device="cpu")
     g = torch.Generator().manual_seed(1)
     mel = torch.randn(nb, t, 64, generator=g) * 2.0 - 4.0
     with torch.no_grad():
         ref = voc(mel)
     got = mine(mel)
+    assert (ref.abs() > 0.999).float().mean() < 0.1, "reference output saturates the final tanh: the comparison would be vacuous"
     assert got.shape == ref.shape and got.shape[0] == nb and got.shape[1] >= t * 160 and got.dtype == torch.float32
     assert rel(got, ref) < 3e-2            # bf16 storage between ~50 layers; a wrong tap / phase / slope gives O(1)
     one = mine(mel[0])                     # un-batched surface, like SpeechT5HifiGan.forward
