@@ -29,6 +29,8 @@ from .ops import PackedWeight
 
 Tensor = torch.Tensor
 LATENT_C_PAD = 64          # conv_in input channels 8 -> one 64-channel K block
+# ff.net.2 + proj_out as one GEMM in the sampling engine (B200_FFPROJ=0: two launches, as the fine-tuning walk keeps them)
+FFPROJ_FUSED = os.environ.get("B200_FFPROJ", "1") != "0"
 
 
 class Arena:
@@ -238,6 +240,13 @@ class UNetEngine:
                 W[b + ".ff.net.0.proj.ln"] = self._ln_pack(sd[b + ".ff.net.0.proj.weight"], sd[b + ".ff.net.0.proj.bias"],
                                                            sd[b + ".norm3.weight"], sd[b + ".norm3.bias"], mt, c, geglu=True)
             W[b + ".ff.net.2"] = self._pw([sd[b + ".ff.net.2.weight"]], sd[b + ".ff.net.2.bias"], mt, 1, 4 * c)
+            if FFPROJ_FUSED:
+                # ff.net.2 (+ the block's residual) and Transformer2DModel.proj_out compose exactly -- nothing non-linear sits
+                # between them:  proj_out(x + W2 g + b2) = (Wp W2) g + Wp x + (Wp b2 + bp).  One GEMM over the K segments
+                # [g | x] replaces two launches and the token tensor between them (same FLOPs: C x 5C per row either way).
+                wp, bp = sd[t.name + ".proj_out.weight"][:, :, 0, 0].float(), sd[t.name + ".proj_out.bias"].float()
+                w2, b2 = sd[b + ".ff.net.2.weight"].float(), sd[b + ".ff.net.2.bias"].float()
+                W[t.name + ".ffout_proj"] = self._pw([wp @ w2, wp], wp @ b2 + bp, mt, 1, 4 * c, c)
 
         lvl_of: Dict[str, int] = {}
         conv3("conv_in", 0, LATENT_C_PAD)
@@ -788,6 +797,10 @@ class _Runner:
             ops.layernorm(tok, M, c, S[b + ".norm3.weight"], S[b + ".norm3.bias"], 1e-5, ln)
             ffh = self.linear(b + ".ff.net.0.proj", ln, lvl)
             ar.release(ln)
+        if t.name + ".ffout_proj" in W:
+            out = self.linear(t.name + ".ffout_proj", ffh, lvl, a1=tok, residual=x, gn_next=True)
+            ar.release(ffh); ar.release(tok)
+            return out
         new_tok = self.linear(b + ".ff.net.2", ffh, lvl, residual=tok)
         ar.release(ffh); ar.release(tok)
         out = self.linear(t.name + ".proj_out", new_tok, lvl, residual=x, gn_next=True)
