@@ -44,7 +44,8 @@ struct AttnParams {
   float scale_log2;         // scale * log2(e)
   __nv_bfloat16* out;
   int out_ld;               // heads * d
-  int variant;              // bit0/bit1: descriptor-convention debug knobs; bit2: fp32 exp2 (one MUFU op per element)
+  int variant;              // bit0/bit1: descriptor-convention debug knobs; bit2: flips the packed / fp32 exp2 choice;
+                            // bit3 / bit4 (host side): force the single-buffered / the pipelined form
   float* lse;               // optional [batch, heads, seq] fp32: log2-domain log-sum-exp of the scaled scores (training)
 };
 
@@ -68,6 +69,22 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
 template <bool kMasked, int KV>
 __device__ __forceinline__ float row_max(uint32_t t_row, int kvalid) {
   float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  if constexpr (KV == 32) {
+    uint32_t r0[32];
+    tmem_ld_x32(t_row, r0);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] = __uint_as_float(r0[i + u]);
+        if (kMasked && i + u >= kvalid) a[u] = -INFINITY;
+      }
+      m0 = fmaxf(m0, a[0]); m1 = fmaxf(m1, a[1]); m2 = fmaxf(m2, a[2]); m3 = fmaxf(m3, a[3]);
+    }
+    return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  } else {
 #pragma unroll
   for (int c = 0; c < KV / 32; c += 2) {
     uint32_t r0[32], r1[32];
@@ -88,6 +105,7 @@ __device__ __forceinline__ float row_max(uint32_t t_row, int kvalid) {
     }
   }
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  }
 }
 
 // One pass over a KV-column S row: p = exp2(s * scale - ref) as bf16 into the K-major core-matrix smem tile.
@@ -147,7 +165,7 @@ __device__ long long s_tl[48];
 #define ATL(i) do {} while (0)
 #endif
 
-template <int D, int KV>
+template <int D, int KV, bool PIPE>
 __global__ void __launch_bounds__(kAttnThreads)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmKs, const AttnParams p) {
@@ -168,17 +186,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   constexpr int kPBytes = kQ * kKV * 2;
   constexpr int kStageBytes = 2 * kKVTile + kOnesBytes;         // K tile, V tile, ones columns
   constexpr int kOCols = D + 16;                // O accumulator columns: d outputs + the denominator (x16)
+  // PIPE: software-pipelined form.  S (TMEM) and P (smem) are double-buffered, so the MMA warp issues QK^T of block
+  // j + 2 as soon as the softmax has finished READING S of block j, and P V of block j while the softmax works on block
+  // j + 1: the softmax warps never wait for a tensor-core hand-off (the per-CTA chain QK^T -> softmax -> P V -> QK^T was
+  // what paced the single-buffered form: ~1000 of every 2400 cycles per 64 keys; profiles/r02_attn_timeline.md).  With
+  // half the keys per block the two S buffers take the TMEM columns of the single one, so the CTAs per SM stay.
+  constexpr bool kPipe = PIPE;
+  constexpr int kBufs = kPipe ? 2 : 1;
   uint8_t* sQ = smem;
-  uint8_t* sP = sQ + kTileBytes;
-  uint8_t* sKV = sP + kPBytes;                  // stages x {K, V, ones}
+  uint8_t* sP = sQ + kTileBytes;                // kBufs x P tile
+  uint8_t* sKV = sP + kBufs * kPBytes;          // stages x {K, V, ones}
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + p.stages * kStageBytes);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                 // [4]
   uint64_t* kv_empty = bars + 5;                // [4]
-  uint64_t* s_full = bars + 9;
-  uint64_t* p_full = bars + 10;
-  uint64_t* o_full = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* s_full = bars + 9;                  // [2]: per S buffer
+  uint64_t* p_full = bars + 11;                 // [2]: per P buffer
+  uint64_t* o_full = bars + 13;                 // [2]: P V of the block that used P buffer i has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -201,9 +226,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
+    }
     fence_barrier_init();
   }
   // the ones columns behind every V tile (never overwritten: the TMA box covers the V tile only)
@@ -225,8 +252,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   pdl_launch_dependents();
   pdl_wait();
   if (warp == 0) ATL(2);
-  const uint32_t t_s = tmem_base;               // S: columns [0, KV)
-  const uint32_t t_o = tmem_base + KV;          // O: columns [KV, KV + D + 16)
+  const uint32_t t_s = tmem_base;               // S: columns [0, KV) (pipelined form: two buffers, [0, 2 KV))
+  const uint32_t t_o = tmem_base + kBufs * KV;  // O: the D + 16 columns behind S
 
   if (warp == 4) {
     // ============================================================ TMA producer
@@ -269,15 +296,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       const uint32_t q_addr = smem_u32(sQ);
       const uint32_t p_addr = smem_u32(sP);
       mbar_wait(q_full, 0);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < p.nblk; ++j) {
-        const uint32_t k_addr = smem_u32(sKV + s * kStageBytes);
-        const uint32_t v_addr = k_addr + kKVTile;
-        mbar_wait(&kv_full[s], ph);
+      // S_buf = Q K_blk^T for the key block in ring stage `st` (whose kv_full phase is `phs`)
+      auto issue_qk = [&](int st, uint32_t phs, int buf) {
+        const uint32_t k_addr = smem_u32(sKV + st * kStageBytes);
+        mbar_wait(&kv_full[st], phs);
         tc_fence_after();
-        if (j < 4) ATL(8 + j);                  // K/V block j landed
-        // S = Q K^T   (the previous block's softmax finished reading S before it released p_full)
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < D / 16; ++k) {
@@ -286,26 +309,63 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                                          : make_smem_desc(q_addr + k * 4096, q_lbo, q_sbo, SWZ_NONE);
             const uint64_t b_desc = kSwz ? make_smem_desc(k_addr + k * 32, 16, kSwzSbo, kSwzMode)
                                          : make_smem_desc(k_addr + k * 2 * kChunk, k_lbo, k_sbo, SWZ_NONE);
-            umma_bf16_ss(t_s, a_desc, b_desc, idesc_s, k != 0);
+            umma_bf16_ss(t_s + buf * KV, a_desc, b_desc, idesc_s, k != 0);
           }
-          umma_commit(s_full);
+          umma_commit(&s_full[buf]);
         }
-        // O += P [V | 1]   (the softmax threads rescaled O, if needed, before they released p_full)
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
+      };
+      // O += P_buf [V | 1] with the V tile of ring stage `st`; frees the stage
+      auto issue_pv = [&](int st, int buf, int j) {
+        const uint32_t v_addr = smem_u32(sKV + st * kStageBytes) + kKVTile;
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < kKV / 16; ++k) {
-            const uint64_t a_desc = make_smem_desc(p_addr + k * 4096, q_lbo, q_sbo, SWZ_NONE);
+            const uint64_t a_desc = make_smem_desc(p_addr + buf * kPBytes + k * 4096, q_lbo, q_sbo, SWZ_NONE);
             const uint64_t b_desc = make_smem_desc(v_addr + k * 256, v_lbo, v_sbo, SWZ_NONE);
             umma_bf16_ss(t_o, a_desc, b_desc, idesc_o, (j | k) != 0);
           }
-          umma_commit(o_full);
-          umma_commit(&kv_empty[s]);
+          umma_commit(&o_full[buf]);
+          umma_commit(&kv_empty[st]);
         }
-        if (++s == p.stages) {
-          s = 0;
-          ph ^= 1;
+      };
+      if (kPipe) {
+        // ring cursors: `sq` walks the blocks whose QK^T is issued (two ahead), `sv` the blocks whose P V is issued
+        int sq = 0, sv = 0;
+        uint32_t phq = 0;
+        auto adv = [&](int& st, uint32_t& phs) { if (++st == p.stages) { st = 0; phs ^= 1; } };
+        uint32_t phv_unused = 0;
+        for (int jj = 0; jj < 2 && jj < p.nblk; ++jj) {
+          issue_qk(sq, phq, jj);
+          if (jj < 4) ATL(8 + jj);
+          adv(sq, phq);
+        }
+        for (int j = 0; j < p.nblk; ++j) {
+          const int buf = j & 1;
+          mbar_wait(&p_full[buf], (j >> 1) & 1);             // P_j written (and S_buf read, O rescaled if needed)
+          tc_fence_after();
+          issue_pv(sv, buf, j);
+          adv(sv, phv_unused);
+          if (j + 2 < p.nblk) {
+            issue_qk(sq, phq, buf);                          // S_buf is free: the softmax of block j has read it
+            if (j + 2 < 4) ATL(8 + j + 2);
+            adv(sq, phq);
+          }
+        }
+      } else {
+        int st = 0;
+        uint32_t ph = 0;
+        for (int j = 0; j < p.nblk; ++j) {
+          // S = Q K^T   (the previous block's softmax finished reading S before it released p_full)
+          issue_qk(st, ph, 0);
+          if (j < 4) ATL(8 + j);                  // K/V block j landed
+          // O += P [V | 1]   (the softmax threads rescaled O, if needed, before they released p_full)
+          mbar_wait(&p_full[0], j & 1);
+          tc_fence_after();
+          issue_pv(st, 0, j);
+          if (++st == p.stages) {
+            st = 0;
+            ph ^= 1;
+          }
         }
       }
     }
@@ -319,48 +379,62 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     // exponentials to an FMA-pipe polynomial (FlashAttention-4) or replacing F2FP by integer packing made this kernel
     // SLOWER (80 / 66 us): ncu shows it bound by the tcgen05.ld -> exp -> st.shared dependency chain of each thread
     // (long-scoreboard + fixed-latency stalls, issue slots 39 % busy), not by the XU pipe.  variant bit 2 flips the default.
-    const bool packed = ((p.variant & 4) == 0) != (KV == 64);
-    uint8_t* sp_row = sP + row * 16;
+    const bool packed = ((p.variant & 4) == 0) != (KV <= 64);
     float ref = 0.f;                              // reference maximum, in exponent units: m_ref * scale * log2(e)
     for (int j = 0; j < p.nblk; ++j) {
       const int kvalid = min(kKV, p.seq - j * kKV);
       const bool full = kvalid == kKV;
-      mbar_wait(s_full, j & 1);
+      // S / P buffer of this block, and which completion of its barriers belongs to it
+      const int buf = kPipe ? (j & 1) : 0;
+      const uint32_t par = kPipe ? ((j >> 1) & 1) : (j & 1);
+      const uint32_t t_sj = t_s + buf * KV + lane_off;
+      uint8_t* sp_row = sP + buf * kPBytes + row * 16;
+      mbar_wait(&s_full[buf], par);
       tc_fence_after();
       if (warp == 0 && j < 4) ATL(16 + j);      // S_j complete
       if (j == 0) {
-        const float mx = full ? row_max<false, KV>(t_s + lane_off, kvalid) : row_max<true, KV>(t_s + lane_off, kvalid);
+        const float mx = full ? row_max<false, KV>(t_sj, kvalid) : row_max<true, KV>(t_sj, kvalid);
         ref = mx * p.scale_log2;
-      } else {
-        // sP is free again (and O is quiescent) once the previous block's P V has completed
-        mbar_wait(o_full, (j - 1) & 1);
+      }
+      if (j >= kBufs) {
+        // this P buffer is free again once the P V of the block that used it last (j - kBufs) has completed (single
+        // buffer: O is then quiescent as well)
+        mbar_wait(&o_full[buf], par ^ 1);
         tc_fence_after();
       }
       float over;
-      if (packed) over = full ? exp_store<false, true, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
-                              : exp_store<true, true, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid);
-      else over = full ? exp_store<false, false, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
-                       : exp_store<true, false, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid);
+      if (packed) over = full ? exp_store<false, true, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid)
+                              : exp_store<true, true, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid);
+      else over = full ? exp_store<false, false, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid)
+                       : exp_store<true, false, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid);
       // warp-uniform decision (the TMEM loads / stores below are warp-collective)
       if (__any_sync(0xffffffffu, over > kRescaleThreshold)) {
         // rare: a row's maximum moved by more than 2^8 -> every row of the warp takes its current maximum as the
         // new reference, O (with its denominator column) is rescaled, and the block's probabilities are redone
-        const float mx = full ? row_max<false, KV>(t_s + lane_off, kvalid) : row_max<true, KV>(t_s + lane_off, kvalid);
+        if (kPipe && j >= 1) {
+          // O must be quiescent: the P V of block j - 1 (other buffer) may still be running
+          mbar_wait(&o_full[buf ^ 1], ((j - 1) >> 1) & 1);
+          tc_fence_after();
+        }
+        const float mx = full ? row_max<false, KV>(t_sj, kvalid) : row_max<true, KV>(t_sj, kvalid);
         const float new_ref = fmaxf(ref, mx * p.scale_log2);
         scale_o(t_o + lane_off, kOCols, ex2_approx(ref - new_ref));
         ref = new_ref;
-        if (packed) (void)(full ? exp_store<false, true, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
-                                : exp_store<true, true, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid));
-        else (void)(full ? exp_store<false, false, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid)
-                         : exp_store<true, false, KV>(t_s + lane_off, sp_row, p.scale_log2, -ref, kvalid));
+        if (packed) (void)(full ? exp_store<false, true, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid)
+                                : exp_store<true, true, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid));
+        else (void)(full ? exp_store<false, false, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid)
+                         : exp_store<true, false, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid));
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[buf]);
       if (warp == 0 && j < 4) ATL(24 + j);      // P_j written
       if (warp == 0 && j == p.nblk - 1) ATL(32);
     }
-    mbar_wait(o_full, (p.nblk - 1) & 1);
+    {
+      const int jl = p.nblk - 1;                // the last P V (commits complete in issue order: all earlier ones too)
+      mbar_wait(&o_full[kPipe ? (jl & 1) : 0], kPipe ? ((jl >> 1) & 1) : (jl & 1));
+    }
     tc_fence_after();
     if (warp == 0) ATL(33);                     // last P V complete
     // epilogue: O[:, :d] / O[:, d]
@@ -410,30 +484,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 #endif
 }
 
-template <int D, int KV>
+template <int D, int KV, bool PIPE>
 static int launch_attention(const CUtensorMap& tm_pieces, const CUtensorMap& tmkv, const void* qkv, AttnParams& p, cudaStream_t stream) {
   constexpr int kTileBytes = 128 * D * 2;
   constexpr int kStageBytes = 2 * KV * D * 2 + 2 * KV * 16;
-  const int fixed = kTileBytes + kQ * KV * 2 + 128 /*barriers*/ + 1024 /*align*/;
+  constexpr int kMinStages = PIPE ? 2 : 1;      // the pipelined form issues two QK^T before the first P V frees a stage
+  const int fixed = kTileBytes + (PIPE ? 2 : 1) * kQ * KV * 2 + 128 /*barriers*/ + 1024 /*align*/;
   // resident CTAs per SM are set by TMEM: 512 / tmem_cols (4, 2 or 1); give each its share of shared memory.  The K/V
   // ring wants >= 2 stages: with one, the next block's loads start only after the current block's P V has completed (the
   // CTA timeline showed exactly that at head_dim 48: profiles/r02_attn_timeline.md), so a fourth co-resident CTA is given
   // up when its share of shared memory would leave a single stage.
   int per_sm = 512 / p.tmem_cols;
   int budget = (220 * 1024) / per_sm;
-  if (per_sm >= 4 && fixed + 2 * kStageBytes > budget) {
+  while (per_sm > 1 && fixed + (per_sm >= 4 ? 2 : kMinStages) * kStageBytes > budget) {
     --per_sm;
     budget = (220 * 1024) / per_sm;
   }
   p.stages = (budget - fixed) / kStageBytes;
   if (p.stages > 4) p.stages = 4;
-  if (p.stages < 1) p.stages = 1;
+  if (p.stages < kMinStages) p.stages = kMinStages;
   static const int dbg_stages = getenv("B200_ATTN_STAGES") ? atoi(getenv("B200_ATTN_STAGES")) : 0;       // A/B knob
-  if (dbg_stages > 0 && dbg_stages < p.stages) p.stages = dbg_stages;
+  if (dbg_stages >= kMinStages && dbg_stages < p.stages) p.stages = dbg_stages;
   const int smem_bytes = fixed + p.stages * kStageBytes;
+  if (smem_bytes > 227 * 1024) return fail(B200_ERR_UNSUPPORTED, "attention: %d bytes of shared memory needed", smem_bytes);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<D, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<D, KV, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(B200_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
@@ -451,8 +527,8 @@ static int launch_attention(const CUtensorMap& tm_pieces, const CUtensorMap& tmk
     if (rc) return rc;
   }
   dim3 grid((p.seq + kQ - 1) / kQ, p.batch * p.heads);
-  B200_CHECK_PDL("attention", launch_pdl(attention_kernel<D, KV>, grid, dim3(kAttnThreads), (size_t)smem_bytes, stream, 0, tm,
-                                         tmkv, tmks, p));
+  B200_CHECK_PDL("attention", launch_pdl(attention_kernel<D, KV, PIPE>, grid, dim3(kAttnThreads), (size_t)smem_bytes, stream, 0,
+                                         tm, tmkv, tmks, p));
   return B200_OK;
 }
 
@@ -483,11 +559,21 @@ static int attention_impl(const void* qkv, void* out, float* lse, int batch, int
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.seq = seq; p.heads = heads; p.d = head_dim; p.batch = batch;
+  // Keys per block.  Single-buffered form: 64 for head_dim <= 48, else 128 (B200_ATTN_KV=128 forces 128).  Pipelined
+  // form: two S / P buffers of HALF as many keys -- the same TMEM columns, so the same CTAs per SM (B200_ATTN_PIPE=2: two
+  // buffers of the single-buffered width; 0: never; 1: always).  Default (measured on B200, tools/attn_ab.py,
+  // profiles/r02_attn_pipe.md): pipelined for head_dim >= 64 when there is more than one single-buffered block
+  // (b32 s3000 d64: 1388 -> 992 us, s188 d160: 60.6 -> 41.4 us, s752 d96 equal); single-buffered for head_dim 32 / 48,
+  // where four co-resident CTAs already overlap each other's hand-offs and the SM's MUFU pipe and shared-memory
+  // bandwidth are what is left (s1000 d32: 60.2 pipelined vs 58.1 us), and for one-block problems (s64 d80: 11.7 vs 9.5).
   static const int kv_env = getenv("B200_ATTN_KV") ? atoi(getenv("B200_ATTN_KV")) : 0;     // A/B knob: 64 or 128
-  const int kv = (head_dim <= 48 && kv_env != 128) ? 64 : 128;
+  static const int pipe_env = getenv("B200_ATTN_PIPE") ? atoi(getenv("B200_ATTN_PIPE")) : -1;
+  const int kv1 = (head_dim <= 48 && kv_env != 128) ? 64 : 128;
+  const int pipe = (variant & 8) ? 0 : (variant & 16) ? 1 : pipe_env >= 0 ? pipe_env : (head_dim >= 64 && seq > kv1) ? 1 : 0;
+  const int kv = pipe == 1 ? kv1 / 2 : kv1;
   p.nblk = (seq + kv - 1) / kv;
   int cols = 32;
-  while (cols < kv + head_dim + 16) cols *= 2;
+  while (cols < (pipe ? 2 : 1) * kv + head_dim + 16) cols *= 2;
   p.tmem_cols = cols;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
@@ -504,13 +590,21 @@ static int attention_impl(const void* qkv, void* out, float* lse, int batch, int
     int rc = make_tmap_bf16(which ? &tmkv : &tm, qkv, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
   }
+#define B200_ATTN_CASE(D_, KVS_, KVP_, KVP2_)                                                                         \
+  case D_:                                                                                                           \
+    if (!pipe) return kv == KVS_ ? launch_attention<D_, KVS_, false>(tm, tmkv, qkv, p, stream)                       \
+                                 : launch_attention<D_, 128, false>(tm, tmkv, qkv, p, stream);                       \
+    if (kv == KVP_) return launch_attention<D_, KVP_, true>(tm, tmkv, qkv, p, stream);                               \
+    if (kv == KVP2_) return launch_attention<D_, KVP2_, true>(tm, tmkv, qkv, p, stream);                             \
+    return fail(B200_ERR_UNSUPPORTED, "attention: no pipelined kernel for head_dim %d with %d-key blocks", D_, kv);
   switch (head_dim) {
-    case 32: return kv == 64 ? launch_attention<32, 64>(tm, tmkv, qkv, p, stream) : launch_attention<32, 128>(tm, tmkv, qkv, p, stream);
-    case 48: return kv == 64 ? launch_attention<48, 64>(tm, tmkv, qkv, p, stream) : launch_attention<48, 128>(tm, tmkv, qkv, p, stream);
-    case 64: return launch_attention<64, 128>(tm, tmkv, qkv, p, stream);
-    case 80: return launch_attention<80, 128>(tm, tmkv, qkv, p, stream);
-    case 96: return launch_attention<96, 128>(tm, tmkv, qkv, p, stream);
-    case 160: return launch_attention<160, 128>(tm, tmkv, qkv, p, stream);
+    B200_ATTN_CASE(32, 64, 32, 64)
+    B200_ATTN_CASE(48, 64, 32, 64)
+    B200_ATTN_CASE(64, 128, 64, 128)
+    B200_ATTN_CASE(80, 128, 64, 128)
+    B200_ATTN_CASE(96, 128, 64, 128)
+    B200_ATTN_CASE(160, 128, 64, 128)
     default: return fail(B200_ERR_UNSUPPORTED, "attention: head_dim %d unsupported (32/48/64/80/96/160)", head_dim);
   }
+#undef B200_ATTN_CASE
 }
