@@ -58,6 +58,8 @@ _PROTOS = {
                                     c_int, c_void_p, c_void_p]),
     "b200_softmax_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_long, c_void_p, c_long, c_float, c_void_p]),
     "b200_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "b200_embed_layernorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_float, c_void_p, c_void_p]),
     "b200_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "b200_time_class_embed": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -120,7 +120,7 @@ struct ConvGemmParams {
   // dh0 = -(k - 1) / 2 * dilation, dh_step = dilation; one phase of a transposed 1-D conv: dh0 = b, dh_step = -1.
   int dh0, dw0, dw_end, dh_step;
   // kAct (b200_conv1d): out = act(acc + bias + unact(residual)).  act: LeakyReLU max(v, act_slope v) (slope 1 = identity) or,
-  // act_tanh, tanh(v).  The residual tensor may itself be stored POST-activation (y = lrelu(x, s)): x = min(y, y / s) is
+  // act_tanh = 1, tanh(v), or, act_tanh = 2, the exact-erf GELU.  The residual tensor may itself be stored POST-activation (y = lrelu(x, s)): x = min(y, y / s) is
   // recovered on the fly with res_neg_gain = 1 / s (1 = the residual is stored as it is).
   float act_slope;
   float res_neg_gain;
@@ -201,7 +201,10 @@ __device__ __forceinline__ void add_res8_unact(float (&v)[8], const uint4 rr, fl
   for (int j = 0; j < 8; ++j) v[j] += fminf(r[j], r[j] * neg_gain);      // neg_gain >= 1: only negative values are scaled
 }
 __device__ __forceinline__ void act8(float (&v)[8], float slope, int use_tanh) {
-  if (use_tanh) {
+  if (use_tanh == 2) {                                                   // exact-erf GELU (b200_conv1d act_tanh = 2)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+  } else if (use_tanh) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float e = __expf(2.0f * fminf(fmaxf(v[j], -15.f), 15.f));     // tanh(x) = 1 - 2 / (e^{2x} + 1)
@@ -991,7 +994,7 @@ struct Conv1dOpts {
   long out_batch_stride;   // elements between images of the output (0: m_h * out_ld)
   float act_slope;         // LeakyReLU slope applied after bias / residual (1: identity)
   float res_neg_gain;      // residual stored post-LeakyReLU(s): 1 / s; plain residual: 1
-  int act_tanh;            // tanh instead of LeakyReLU
+  int act_tanh;            // 1: tanh, 2: exact-erf GELU instead of LeakyReLU
 };
 
 // C-ABI: see include/b200ldm.h

@@ -472,6 +472,58 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int M, int C, const float*
   else layernorm_rows<kLnMaxVec, 1>(x, row0, M, C, gamma, beta, eps, y, lane);
 }
 
+// Token embedding of a RoBERTa-style text encoder (the CLAP text tower in front of the pipeline):
+//   y[row] = LayerNorm(word[ids[row]] + pos[pos_ids[row]] + type0) as bf16; fp32 tables, one warp per token row, C % 4 == 0.
+// Three passes over the (L2-resident) table rows instead of registers: the row count is a few hundred per call.
+__global__ void __launch_bounds__(256)
+embed_layernorm_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids, int M, int C, int vocab, int npos,
+                       const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type0,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                       __nv_bfloat16* __restrict__ y) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (row >= M) return;
+  const int id = min(max(ids[row], 0), vocab - 1), pi = min(max(pos_ids[row], 0), npos - 1);
+  const float4* w4 = reinterpret_cast<const float4*>(word + static_cast<size_t>(id) * C);
+  const float4* p4 = reinterpret_cast<const float4*>(pos + static_cast<size_t>(pi) * C);
+  const float4* t4 = reinterpret_cast<const float4*>(type0);
+  const int nvec = C / 4;
+  auto load = [&](int v) {
+    const float4 a = w4[v], b = p4[v], c = t4[v];
+    // the reference's order of additions: (word + type) + position
+    return make_float4((a.x + c.x) + b.x, (a.y + c.y) + b.y, (a.z + c.z) + b.z, (a.w + c.w) + b.w);
+  };
+  float s = 0.f;
+  for (int v = lane; v < nvec; v += 32) {
+    const float4 e = load(v);
+    s += (e.x + e.y) + (e.z + e.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+  for (int v = lane; v < nvec; v += 32) {
+    const float4 e = load(v);
+    const float d0 = e.x - mean, d1 = e.y - mean, d2 = e.z - mean, d3 = e.w - mean;
+    q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+  __nv_bfloat16* out = y + static_cast<size_t>(row) * C;
+  for (int v = lane; v < nvec; v += 32) {
+    const float4 e = load(v);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + v * 4);
+    const float4 b = *reinterpret_cast<const float4*>(beta + v * 4);
+    uint2 o;
+    o.x = pack_bf16x2((e.x - mean) * rstd * g.x + b.x, (e.y - mean) * rstd * g.y + b.y);
+    o.y = pack_bf16x2((e.z - mean) * rstd * g.z + b.z, (e.w - mean) * rstd * g.w + b.w);
+    *reinterpret_cast<uint2*>(out + v * 4) = o;
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -624,5 +676,19 @@ extern "C" int b200_layernorm(const void* x, int m, int c, const float* gamma, c
     B200_CHECK_PDL("layernorm", launch_pdl(layernorm_kernel<kLnRows>, dim3(nblk), dim3(warps_per_block * 32), 0, stream, 0,
                                            reinterpret_cast<const __nv_bfloat16*>(x), m, c, gamma, beta, eps,
                                            reinterpret_cast<__nv_bfloat16*>(y)));
+  return B200_OK;
+}
+
+extern "C" int b200_embed_layernorm(const int* ids, const int* pos_ids, int m, int c, int vocab, int npos, const float* word,
+                                    const float* pos, const float* type0, const float* gamma, const float* beta, float eps,
+                                    void* y, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  B200_CHECK_ARG(ids && pos_ids && word && pos && type0 && gamma && beta && y, "embed_layernorm: null pointer");
+  B200_CHECK_ARG(c > 0 && c % 4 == 0 && vocab > 0 && npos > 0, "embed_layernorm: C=%d vocab=%d npos=%d unsupported", c, vocab, npos);
+  if (m == 0) return B200_OK;
+  const int rows_per_block = 8;
+  B200_CHECK_PDL("embed_layernorm", launch_pdl(embed_layernorm_kernel, dim3((m + rows_per_block - 1) / rows_per_block),
+                                               dim3(rows_per_block * 32), 0, stream, 0, ids, pos_ids, m, c, vocab, npos, word, pos,
+                                               type0, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y)));
   return B200_OK;
 }

@@ -389,6 +389,20 @@ def layernorm(x: Tensor, m: int, c: int, gamma: Tensor, beta: Tensor, eps: float
     return y
 
 
+def embed_layernorm(ids: Tensor, pos_ids: Tensor, word: Tensor, pos: Tensor, type0: Tensor, gamma: Tensor, beta: Tensor,
+                    eps: float, y: Tensor) -> Tensor:
+    """y[row] = LayerNorm(word[ids[row]] + type0 + pos[pos_ids[row]]) as bf16; see include/b200ldm.h::b200_embed_layernorm."""
+    m, c = ids.numel(), word.shape[1]
+    assert ids.dtype == torch.int32 and pos_ids.dtype == torch.int32 and pos_ids.numel() == m
+    for t in (word, pos, type0, gamma, beta):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert y.dtype == torch.bfloat16 and y.numel() == m * c and pos.shape[1] == c and type0.numel() == c
+    info = {"desc": f"m{m} c{c}", "bytes": 14.0 * m * c} if _lib.PROFILE is not None else None
+    call("b200_embed_layernorm", ptr(ids), ptr(pos_ids), m, c, word.shape[0], pos.shape[0], ptr(word), ptr(pos), ptr(type0),
+         ptr(gamma), ptr(beta), float(eps), ptr(y), stream(), info=info)
+    return y
+
+
 def attention(qkv: Tensor, out: Tensor, batch: int, seq: int, heads: int, head_dim: int,
               scale: Optional[float] = None, variant: int = 0) -> Tensor:
     assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
@@ -582,7 +596,8 @@ def conv1d(pw: PackedWeight, x: Tensor, nb: int, length: int, out: Tensor, *, dh
            act_tanh: bool = False, out_ld: Optional[int] = None, out_batch_stride: int = 0,
            cta_pair: Optional[bool] = None) -> Tensor:
     """One Conv1d (or one output phase of a ConvTranspose1d) over time-major x [nb, length, c]; see
-    include/b200ldm.h::b200_conv1d.  residual is stored post-LeakyReLU(res_slope) (1.0: plain)."""
+    include/b200ldm.h::b200_conv1d.  residual is stored post-LeakyReLU(res_slope) (1.0: plain).  act_tanh: False = LeakyReLU
+    (act_slope; 0.0 = ReLU, 1.0 = identity), True = tanh, 2 = exact-erf GELU."""
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() == nb * length * pw.c0 and pw.c1 == 0 and pw.c2 == 0
     rows = length if m_rows is None else m_rows
     out_fp32 = out.dtype == torch.float32

@@ -88,7 +88,8 @@ class _LoopState:
 class AudioLDMPipeline:
     def __init__(self, unet: UNet2DConditionModel, scheduler: Optional[DDIMScheduler] = None, vae=None, vocoder=None,
                  text_encoder=None, tokenizer=None, tail_dtype: torch.dtype = torch.bfloat16, use_cuda_graph: bool = True,
-                 branches: Optional[int] = None, b200_vae: Optional[bool] = None, b200_vocoder: Optional[bool] = None):
+                 branches: Optional[int] = None, b200_vae: Optional[bool] = None, b200_vocoder: Optional[bool] = None,
+                 b200_text_encoder: Optional[bool] = None):
         self.unet = unet
         self.scheduler = scheduler or DDIMScheduler()
         self.vae, self.vocoder = vae, vocoder
@@ -124,6 +125,14 @@ class AudioLDMPipeline:
             self.vocoder = from_torch_vocoder(self.vocoder, self.device)
         if self.vocoder is not None:
             self.vocoder = self.vocoder.to(self.device, tail_dtype).eval()
+        # CLAP text tower: transformers' ClapTextModelWithProjection is re-hosted the same way (clap.B200ClapTextEncoder,
+        # SURVEY 8(f) item 4) unless b200_text_encoder=False / B200_TEXT_ENCODER=0.
+        if b200_text_encoder is None:
+            b200_text_encoder = os.environ.get("B200_TEXT_ENCODER", "1") != "0"
+        if (self.text_encoder is not None and b200_text_encoder and self.device.type == "cuda"
+                and isinstance(self.text_encoder, torch.nn.Module) and type(self.text_encoder).__name__ == "ClapTextModelWithProjection"):
+            from .clap import from_torch_text_encoder
+            self.text_encoder = from_torch_text_encoder(self.text_encoder, self.device)
         nblocks = len(self.vae.config.block_out_channels) if self.vae is not None else 3
         self.vae_scale_factor = 2 ** (nblocks - 1)
         self.last_timing: Dict[str, float] = {}

@@ -96,7 +96,8 @@ int b200_conv3x3_s2_pad01(const void* x, int c, int nb, int h, int w, const void
  *   Phase phi of ConvTranspose1d(k, stride s, padding p): a = (phi + p) % s, b = (phi + p) / s, taps W[:, :, s t + a]^T,
  *   dh0 = b, dh_step = -1, m_rows = ceil((len_out - phi) / s), out = y + phi * c_out, out_ld = s * c_out,
  *   out_batch_stride = len_out * c_out (0: m_rows * out_ld).
- * act: LeakyReLU with slope act_slope in [0, 1] (1 = identity) or, act_tanh != 0, tanh.  HiFi-GAN's residual blocks need
+ * act: LeakyReLU with slope act_slope in [0, 1] (1 = identity, 0 = ReLU) or, act_tanh = 1, tanh, or, act_tanh = 2, the
+ * exact-erf GELU (with ntaps = 1 this is nn.Linear + activation: the layers of the CLAP text encoder, audioldm_with_lora_b200/clap.py).  HiFi-GAN's residual blocks need
  * both x and leaky_relu(x); only y = leaky_relu(x, s) is stored and the residual read recovers x = min(y, y / s):
  * res_neg_gain = 1 / s (1: the residual is stored as it is).  out bf16, or fp32 (out_fp32, contiguous). */
 int b200_conv1d(const void* x, int c, int nb, int len, int ntaps, int dh0, int dh_step, int m_rows, const void* wpacked,
@@ -174,6 +175,15 @@ int b200_softmax_rows(const float* s, int rows, int cols, int cols_pad, long ld_
  * BasicTransformerBlock.norm1/2/3 (diffusers, via train_audioldm_lora.py:539-546). */
 int b200_layernorm(const void* x, int m, int c, const float* gamma, const float* beta, float eps, void* y,
                    void* stream);
+
+/* Token embedding of a RoBERTa-style text encoder: y[row, :] = LayerNorm(word[ids[row]] + type0 + pos[pos_ids[row]]) as bf16
+ * [m, c]; word fp32 [vocab, c], pos fp32 [npos, c], type0 fp32 [c] (token type 0), ids / pos_ids int32 [m] (clamped to the
+ * tables), c % 4 == 0.  Replaces ClapTextEmbeddings.forward (transformers) under ClapTextModelWithProjection, the prompt
+ * encoder of the reference: /root/reference/script/train/train_audioldm_lora.py:368-369, :513-524; inside
+ * AudioLDMPipeline._encode_prompt for app.py:14 / generate_audio.py:47-52. */
+int b200_embed_layernorm(const int* ids, const int* pos_ids, int m, int c, int vocab, int npos, const float* word,
+                         const float* pos, const float* type0, const float* gamma, const float* beta, float eps, void* y,
+                         void* stream);
 
 /* Fused multi-head self-attention softmax(Q K^T * scale) V over the latent sequence.
  * qkv: bf16 [batch, seq, 3*heads*head_dim] = [Q | K | V] columns, head-major inside each;

@@ -426,7 +426,7 @@ def install(monkeypatch, ops_module):
     for name in ("conv_gemm", "groupnorm_silu", "layernorm", "attention", "time_class_embed",
                  "pack_nchw_to_nhwc", "unpack_nhwc_to_nchw", "upsample_nearest", "sampler_step", "add_noise",
                  "adamw_flat", "mse_partial", "set_sm_budget", "gn_stat_slabs", "groupnorm_apply", "linear_lora_ok", "linear_lora", "linear_ln", "linear_stats",
-                 "conv1d", "lrelu_mean3", "f32_to_bf16", "gemm_nt", "softmax_rows", "conv3x3_s2_pad01") + TRAIN_OPS:
+                 "conv1d", "lrelu_mean3", "embed_layernorm", "f32_to_bf16", "gemm_nt", "softmax_rows", "conv3x3_s2_pad01") + TRAIN_OPS:
         monkeypatch.setattr(ops_module, name, globals()[name])
 
 
@@ -452,13 +452,22 @@ def conv1d(pw, x, nb, length, out, *, dh0, dh_step, m_rows=None, residual=None, 
     if residual is not None:
         r = residual.view(nb, length, pw.n_valid).float()
         acc = acc + torch.minimum(r, r / res_slope)
-    acc = torch.tanh(acc) if act_tanh else torch.maximum(acc, acc * act_slope)
+    if int(act_tanh) == 2:
+        acc = torch.nn.functional.gelu(acc)
+    else:
+        acc = torch.tanh(acc) if act_tanh else torch.maximum(acc, acc * act_slope)
     ld = out_ld if out_ld is not None else pw.n_valid
     bs = out_batch_stride if out_batch_stride else rows * ld
     flat = out.view(-1)
     idx = (torch.arange(nb)[:, None, None] * bs + torch.arange(rows)[None, :, None] * ld + torch.arange(pw.n_valid)[None, None, :])
     flat[idx.reshape(-1)] = acc.reshape(-1).to(out.dtype)
     return out
+
+
+def embed_layernorm(ids, pos_ids, word, pos, type0, gamma, beta, eps, y):
+    e = (word[ids.long()] + type0) + pos[pos_ids.long()]
+    y.copy_(torch.nn.functional.layer_norm(e, (word.shape[1],), gamma, beta, eps).to(y.dtype).view_as(y))
+    return y
 
 
 def lrelu_mean3(a0, a1, a2, in_slope, out_slope, y):
