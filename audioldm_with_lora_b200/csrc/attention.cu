@@ -26,6 +26,16 @@
 #include "host_util.h"
 #include "ptx.cuh"
 
+#ifndef B200_ATTN_NOEXP
+#define B200_ATTN_NOEXP 0
+#endif
+#ifndef B200_ATTN_NOSTORE
+#define B200_ATTN_NOSTORE 0
+#endif
+#ifndef B200_ATTN_NOPV
+#define B200_ATTN_NOPV 0
+#endif
+
 namespace b200 {
 
 static constexpr int kQ = 128;                 // query rows per CTA
@@ -45,7 +55,7 @@ struct AttnParams {
   __nv_bfloat16* out;
   int out_ld;               // heads * d
   int variant;              // bit0/bit1: descriptor-convention debug knobs; bit2: flips the packed / fp32 exp2 choice;
-                            // bit3 / bit4 (host side): force the single-buffered / the pipelined form
+                            // bit3 / bit4 (host side): force the single-buffered / the pipelined form; bit5 / bit6: P through smem / TMEM
   float* lse;               // optional [batch, heads, seq] fp32: log2-domain log-sum-exp of the scaled scores (training)
 };
 
@@ -135,12 +145,57 @@ __device__ __forceinline__ float exp_store(uint32_t t_row, uint8_t* sp_row, floa
         }
         const uint32_t x = pack_bf16x2(x0, x1);
         mx = max_bf16x2(mx, x);
+#if B200_ATTN_NOEXP      // limiter experiment (tools/build_variant.sh; results are garbage): no MUFU work
+        pk[i] = x;
+#else
         pk[i] = kPackedExp ? ex2_bf16x2(x) : pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
+#endif
       }
+#if B200_ATTN_NOSTORE    // limiter experiment: a quarter of the P stores (the P V product still reads the whole tile)
+      if (g == 0)
+#endif
       *reinterpret_cast<uint4*>(sp_row + (c * 4 + g) * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
   return fmaxf(bf16_lo(mx), bf16_hi(mx));
+}
+
+// TMEM form of the same pass (kernel template TS): the bf16 probabilities go back to tensor memory (two per 32-bit column:
+// the layout of a K-major A operand read from TMEM) instead of shared memory, and the block's row sum is kept in fp32
+// registers.  Per 64-key block this takes 16 KB of stores and 16 KB of tensor-core reads off the SM's shared-memory port,
+// which -- not the MUFU pipe, not the copy engine -- is what the kernel ran into (profiles/r02_attn_pipe.md).
+template <bool kMasked, int KV>
+__device__ __forceinline__ float exp_store_tmem(uint32_t t_row, uint32_t t_prow, float scale_log2, float neg_ref, int kvalid,
+                                                float& block_sum) {
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  uint32_t r[2][32];
+  tmem_ld_x32(t_row, r[0]);
+#pragma unroll
+  for (int c = 0; c < KV / 32; ++c) {
+    tmem_wait_ld();
+    if (c + 1 < KV / 32) tmem_ld_x32(t_row + (c + 1) * 32, r[(c + 1) & 1]);
+    const uint32_t(&cur)[32] = r[c & 1];
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int col = c * 32 + 2 * i;
+      float x0 = fmaf(__uint_as_float(cur[2 * i]), scale_log2, neg_ref);
+      float x1 = fmaf(__uint_as_float(cur[2 * i + 1]), scale_log2, neg_ref);
+      if (kMasked) {
+        if (col >= kvalid) x0 = -INFINITY;
+        if (col + 1 >= kvalid) x1 = -INFINITY;
+      }
+      m0 = fmaxf(m0, x0);
+      m1 = fmaxf(m1, x1);
+      const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+      l0 += e0;
+      l1 += e1;
+      pk[i] = pack_bf16x2(e0, e1);
+    }
+    tmem_st_x16(t_prow + c * 16, pk);
+  }
+  block_sum = l0 + l1;
+  return fmaxf(m0, m1);
 }
 
 // O (TMEM, ncols fp32 columns of this thread's row) *= f
@@ -165,7 +220,7 @@ __device__ long long s_tl[48];
 #define ATL(i) do {} while (0)
 #endif
 
-template <int D, int KV, bool PIPE>
+template <int D, int KV, bool PIPE, bool TS = false>
 __global__ void __launch_bounds__(kAttnThreads)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmKs, const AttnParams p) {
@@ -182,7 +237,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   constexpr int kTileBytes = 128 * D * 2;       // the Q tile
   constexpr int kKVTile = KV * D * 2;           // one K / V tile
   constexpr int kChunk = KV * 16;               // bytes between 8-element chunks of a K / V tile
-  constexpr int kOnesBytes = 2 * kChunk;
+  // Swizzled form (head_dim 32 / 64): V too arrives as whole swizzled rows -- a [keys][head_dim] tile with 64- / 128-byte
+  // rows IS the canonical MN-major swizzled operand layout (8 keys x one swizzle span per atom) -- and the denominator is a
+  // second, 16-column MMA per key step against ONE static block of ones.  (With V in 16-byte pieces the kernel could not
+  // drop below 40 us at s1000 d32 even with the exponentials, the P stores and the P V products removed: the copy engine
+  // delivers about one piece per clock per SM; gpurun_out/r02_attn_limiter.log.)
+  constexpr int kOnesBytes = kSwz ? 0 : 2 * kChunk;          // per stage (no-swizzle form: the ones columns follow the V tile)
+  constexpr int kOnesStatic = 512;                            // swizzled form: 16 keys x 16 columns of bf16 1.0
   constexpr int kPBytes = kQ * kKV * 2;
   constexpr int kStageBytes = 2 * kKVTile + kOnesBytes;         // K tile, V tile, ones columns
   constexpr int kOCols = D + 16;                // O accumulator columns: d outputs + the denominator (x16)
@@ -193,9 +254,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   // half the keys per block the two S buffers take the TMEM columns of the single one, so the CTAs per SM stay.
   constexpr bool kPipe = PIPE;
   constexpr int kBufs = kPipe ? 2 : 1;
+  // TS (swizzled form only): P lives in TMEM (KV / 2 columns per buffer, behind the S buffers) and is the tensor core's A
+  // operand from there; the denominator is summed in registers, so O is just the head_dim output columns.
+  constexpr bool kTS = TS;
+  static_assert(!TS || kSwz, "the TMEM-P form is built for the swizzled V layout (head_dim 32 / 64)");
+  constexpr int kPCols = KV / 2;
   uint8_t* sQ = smem;
-  uint8_t* sP = sQ + kTileBytes;                // kBufs x P tile
-  uint8_t* sKV = sP + kBufs * kPBytes;          // stages x {K, V, ones}
+  uint8_t* sP = sQ + kTileBytes;                // kBufs x P tile (not in the TS form)
+  uint8_t* sKV = sP + (kTS ? 0 : kBufs * kPBytes);          // stages x {K, V, ones}
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + p.stages * kStageBytes);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                 // [4]
@@ -233,11 +299,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     }
     fence_barrier_init();
   }
-  // the ones columns behind every V tile (never overwritten: the TMA box covers the V tile only)
-  for (int i = threadIdx.x; i < p.stages * (kOnesBytes / 16); i += kAttnThreads) {
-    const int st = i / (kOnesBytes / 16), off = i % (kOnesBytes / 16);
-    *reinterpret_cast<uint4*>(sKV + st * kStageBytes + 2 * kKVTile + off * 16) =
-        make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  uint8_t* sOnes = reinterpret_cast<uint8_t*>(bars) + 128;
+  if constexpr (kTS) {
+  } else if constexpr (kSwz) {
+    for (int i = threadIdx.x; i < kOnesStatic / 16; i += kAttnThreads)
+      *reinterpret_cast<uint4*>(sOnes + i * 16) = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  } else {
+    // the ones columns behind every V tile (never overwritten: the TMA box covers the V tile only)
+    for (int i = threadIdx.x; i < p.stages * (kOnesBytes / 16); i += kAttnThreads) {
+      const int st = i / (kOnesBytes / 16), off = i % (kOnesBytes / 16);
+      *reinterpret_cast<uint4*>(sKV + st * kStageBytes + 2 * kKVTile + off * 16) =
+          make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    }
   }
   fence_proxy_async_smem();
   if (warp == 4) {
@@ -253,7 +326,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   pdl_wait();
   if (warp == 0) ATL(2);
   const uint32_t t_s = tmem_base;               // S: columns [0, KV) (pipelined form: two buffers, [0, 2 KV))
-  const uint32_t t_o = tmem_base + kBufs * KV;  // O: the D + 16 columns behind S
+  const uint32_t t_p = tmem_base + kBufs * KV;  // TS form: P buffers (KV / 2 columns each)
+  const uint32_t t_o = tmem_base + kBufs * KV + (kTS ? kBufs * kPCols : 0);  // O: the D + 16 (TS: D) columns behind S (and P)
 
   if (warp == 4) {
     // ============================================================ TMA producer
@@ -272,9 +346,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         uint8_t* k_dst = sKV + s * kStageBytes;
         if (elect_one()) {
           mbar_expect_tx(&kv_full[s], 2 * kKVTile);
-          if (kSwz) tma_load_3d(k_dst, &tmKs, &kv_full[s], p.heads * D + h * D, j * kKV, b);
-          else tma_load_4d(k_dst, &tmKV, &kv_full[s], 0, j * kKV, chunk_k, b);
-          tma_load_4d(k_dst + kKVTile, &tmKV, &kv_full[s], 0, j * kKV, chunk_v, b);
+          if (kSwz) {
+            tma_load_3d(k_dst, &tmKs, &kv_full[s], p.heads * D + h * D, j * kKV, b);
+            tma_load_3d(k_dst + kKVTile, &tmKs, &kv_full[s], 2 * p.heads * D + h * D, j * kKV, b);
+          } else {
+            tma_load_4d(k_dst, &tmKV, &kv_full[s], 0, j * kKV, chunk_k, b);
+            tma_load_4d(k_dst + kKVTile, &tmKV, &kv_full[s], 0, j * kKV, chunk_v, b);
+          }
         }
         if (++s == p.stages) {
           s = 0;
@@ -286,7 +364,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     // ============================================================ MMA issuer (whole warp, elected lane issues)
     {
       const uint32_t idesc_s = make_idesc_bf16(128, KV, 0, 0);
-      const uint32_t idesc_o = make_idesc_bf16(128, kOCols, 0, 1);  // B = [V | 1], MN-major
+      const uint32_t idesc_o = make_idesc_bf16(128, kSwz ? D : kOCols, 0, 1);  // B = [V | 1] (swizzled form: V), MN-major
+      const uint32_t idesc_1 = make_idesc_bf16(128, 16, 0, 1);      // swizzled form: B = the static ones block
+      const uint32_t ones_addr = smem_u32(sOnes);
       // no-swizzle canonical layouts: core matrix = 8 rows x 16 B, contiguous (128 B).
       //  K-major tile [R rows][D]: next 8-row group +128 B (SBO), next 8-elem K chunk +R*16 B (LBO); R = 128 (Q, P) or KV (K)
       //  MN-major V   [KV keys][D]: next 8-key group +128 B (LBO), next 8-elem d chunk +KV*16 B (SBO)
@@ -319,10 +399,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         const uint32_t v_addr = smem_u32(sKV + st * kStageBytes) + kKVTile;
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kKV / 16; ++k) {
+          for (int k = 0; k < (B200_ATTN_NOPV ? 1 : kKV / 16); ++k) {      // NOPV: limiter experiment (garbage results)
             const uint64_t a_desc = make_smem_desc(p_addr + buf * kPBytes + k * 4096, q_lbo, q_sbo, SWZ_NONE);
-            const uint64_t b_desc = make_smem_desc(v_addr + k * 256, v_lbo, v_sbo, SWZ_NONE);
-            umma_bf16_ss(t_o, a_desc, b_desc, idesc_o, (j | k) != 0);
+            if (kTS) {
+              // A = P from TMEM: 16 keys = 8 columns of bf16 pairs
+              const uint64_t b_desc = make_smem_desc(v_addr + k * 16 * D * 2, kSwzSbo, kSwzSbo, kSwzMode);
+              umma_bf16_ts(t_o, t_p + buf * kPCols + k * 8, b_desc, idesc_o, (j | k) != 0);
+            } else if (kSwz) {
+              // MN-major swizzled V: 16 keys = two 8-row atoms of D * 2-byte rows (SBO apart); head_dim is one swizzle span
+              const uint64_t b_desc = make_smem_desc(v_addr + k * 16 * D * 2, kSwzSbo, kSwzSbo, kSwzMode);
+              umma_bf16_ss(t_o, a_desc, b_desc, idesc_o, (j | k) != 0);
+              const uint64_t o_desc = make_smem_desc(ones_addr, 128, 256, SWZ_NONE);
+              umma_bf16_ss(t_o + D, a_desc, o_desc, idesc_1, (j | k) != 0);
+            } else {
+              const uint64_t b_desc = make_smem_desc(v_addr + k * 256, v_lbo, v_sbo, SWZ_NONE);
+              umma_bf16_ss(t_o, a_desc, b_desc, idesc_o, (j | k) != 0);
+            }
           }
           umma_commit(&o_full[buf]);
           umma_commit(&kv_empty[st]);
@@ -381,6 +473,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     // (long-scoreboard + fixed-latency stalls, issue slots 39 % busy), not by the XU pipe.  variant bit 2 flips the default.
     const bool packed = ((p.variant & 4) == 0) != (KV <= 64);
     float ref = 0.f;                              // reference maximum, in exponent units: m_ref * scale * log2(e)
+    float lsum = 0.f;                             // TS form: the row's denominator (fp32 sum of the probabilities)
     for (int j = 0; j < p.nblk; ++j) {
       const int kvalid = min(kKV, p.seq - j * kKV);
       const bool full = kvalid == kKV;
@@ -402,8 +495,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         mbar_wait(&o_full[buf], par ^ 1);
         tc_fence_after();
       }
-      float over;
-      if (packed) over = full ? exp_store<false, true, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid)
+      float over, bsum = 0.f;
+      const uint32_t t_pj = t_p + buf * kPCols + lane_off;
+      if (kTS) over = full ? exp_store_tmem<false, KV>(t_sj, t_pj, p.scale_log2, -ref, kvalid, bsum)
+                           : exp_store_tmem<true, KV>(t_sj, t_pj, p.scale_log2, -ref, kvalid, bsum);
+      else if (packed) over = full ? exp_store<false, true, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid)
                               : exp_store<true, true, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid);
       else over = full ? exp_store<false, false, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid)
                        : exp_store<true, false, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid);
@@ -418,14 +514,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         }
         const float mx = full ? row_max<false, KV>(t_sj, kvalid) : row_max<true, KV>(t_sj, kvalid);
         const float new_ref = fmaxf(ref, mx * p.scale_log2);
-        scale_o(t_o + lane_off, kOCols, ex2_approx(ref - new_ref));
+        const float fscale = ex2_approx(ref - new_ref);
+        scale_o(t_o + lane_off, kTS ? D : kOCols, fscale);
+        lsum *= fscale;
         ref = new_ref;
-        if (packed) (void)(full ? exp_store<false, true, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid)
+        if (kTS) (void)(full ? exp_store_tmem<false, KV>(t_sj, t_pj, p.scale_log2, -ref, kvalid, bsum)
+                             : exp_store_tmem<true, KV>(t_sj, t_pj, p.scale_log2, -ref, kvalid, bsum));
+        else if (packed) (void)(full ? exp_store<false, true, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid)
                                 : exp_store<true, true, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid));
         else (void)(full ? exp_store<false, false, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid)
                          : exp_store<true, false, KV>(t_sj, sp_row, p.scale_log2, -ref, kvalid));
       }
-      fence_proxy_async_smem();
+      lsum += bsum;
+      if (kTS) tmem_wait_st();
+      else fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[buf]);
       if (warp == 0 && j < 4) ATL(24 + j);      // P_j written
@@ -439,12 +541,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     if (warp == 0) ATL(33);                     // last P V complete
     // epilogue: O[:, :d] / O[:, d]
     const int qrow = q0 + row;
-    uint32_t rl[16];
-    tmem_ld_x16(t_o + lane_off + D, rl);
-    tmem_wait_ld();
-    const float inv = 1.0f / __uint_as_float(rl[0]);
+    float den = lsum;
+    if (!kTS) {
+      uint32_t rl[16];
+      tmem_ld_x16(t_o + lane_off + D, rl);
+      tmem_wait_ld();
+      den = __uint_as_float(rl[0]);
+    }
+    const float inv = 1.0f / den;
     if (p.lse != nullptr && qrow < p.seq)      // p_ij = exp2(s_ij * scale_log2 - lse): what the backward kernel recomputes
-      p.lse[(static_cast<size_t>(b) * p.heads + h) * p.seq + qrow] = ref + log2f(__uint_as_float(rl[0]));
+      p.lse[(static_cast<size_t>(b) * p.heads + h) * p.seq + qrow] = ref + log2f(den);
     __nv_bfloat16* o = p.out + (static_cast<size_t>(b) * p.seq + qrow) * p.out_ld + h * D;
 #pragma unroll
     for (int c = 0; c < D / 16; ++c) {
@@ -484,12 +590,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 #endif
 }
 
-template <int D, int KV, bool PIPE>
+template <int D, int KV, bool PIPE, bool TS = false>
 static int launch_attention(const CUtensorMap& tm_pieces, const CUtensorMap& tmkv, const void* qkv, AttnParams& p, cudaStream_t stream) {
   constexpr int kTileBytes = 128 * D * 2;
-  constexpr int kStageBytes = 2 * KV * D * 2 + 2 * KV * 16;
+  constexpr bool kSwz = (D == 32 || D == 64);
+  constexpr int kStageBytes = 2 * KV * D * 2 + (kSwz ? 0 : 2 * KV * 16);
   constexpr int kMinStages = PIPE ? 2 : 1;      // the pipelined form issues two QK^T before the first P V frees a stage
-  const int fixed = kTileBytes + (PIPE ? 2 : 1) * kQ * KV * 2 + 128 /*barriers*/ + 1024 /*align*/;
+  const int fixed = kTileBytes + (TS ? 0 : (PIPE ? 2 : 1) * kQ * KV * 2) + 128 /*barriers*/ + (kSwz ? 512 : 0) /*ones*/ + 1024 /*align*/;
   // resident CTAs per SM are set by TMEM: 512 / tmem_cols (4, 2 or 1); give each its share of shared memory.  The K/V
   // ring wants >= 2 stages: with one, the next block's loads start only after the current block's P V has completed (the
   // CTA timeline showed exactly that at head_dim 48: profiles/r02_attn_timeline.md), so a fourth co-resident CTA is given
@@ -509,7 +616,7 @@ static int launch_attention(const CUtensorMap& tm_pieces, const CUtensorMap& tmk
   if (smem_bytes > 227 * 1024) return fail(B200_ERR_UNSUPPORTED, "attention: %d bytes of shared memory needed", smem_bytes);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<D, KV, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<D, KV, PIPE, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(B200_ERR_CUDA, "attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
@@ -527,7 +634,7 @@ static int launch_attention(const CUtensorMap& tm_pieces, const CUtensorMap& tmk
     if (rc) return rc;
   }
   dim3 grid((p.seq + kQ - 1) / kQ, p.batch * p.heads);
-  B200_CHECK_PDL("attention", launch_pdl(attention_kernel<D, KV, PIPE>, grid, dim3(kAttnThreads), (size_t)smem_bytes, stream, 0,
+  B200_CHECK_PDL("attention", launch_pdl(attention_kernel<D, KV, PIPE, TS>, grid, dim3(kAttnThreads), (size_t)smem_bytes, stream, 0,
                                          tm, tmkv, tmks, p));
   return B200_OK;
 }
@@ -562,18 +669,21 @@ static int attention_impl(const void* qkv, void* out, float* lse, int batch, int
   // Keys per block.  Single-buffered form: 64 for head_dim <= 48, else 128 (B200_ATTN_KV=128 forces 128).  Pipelined
   // form: two S / P buffers of HALF as many keys -- the same TMEM columns, so the same CTAs per SM (B200_ATTN_PIPE=2: two
   // buffers of the single-buffered width; 0: never; 1: always).  Default (measured on B200, tools/attn_ab.py,
-  // profiles/r02_attn_pipe.md): pipelined for head_dim >= 64 when there is more than one single-buffered block
-  // (b32 s3000 d64: 1388 -> 992 us, s188 d160: 60.6 -> 41.4 us, s752 d96 equal); single-buffered for head_dim 32 / 48,
-  // where four co-resident CTAs already overlap each other's hand-offs and the SM's MUFU pipe and shared-memory
-  // bandwidth are what is left (s1000 d32: 60.2 pipelined vs 58.1 us), and for one-block problems (s64 d80: 11.7 vs 9.5).
+  // profiles/r02_attn_pipe.md): pipelined for head_dim 32 and >= 64 when there is more than one single-buffered block
+  // (b32 s3000 d64: 1380 -> 956 us, s188 d160: 60.6 -> 41.7 us, s752 d96 equal; b16 s1000 d32: 58.0 -> 54.0 us together
+  // with P through TMEM); single-buffered for head_dim 48 (three co-resident CTAs already overlap each other's hand-offs:
+  // 12.2 vs 12.0 us) and for one-block problems.
   static const int kv_env = getenv("B200_ATTN_KV") ? atoi(getenv("B200_ATTN_KV")) : 0;     // A/B knob: 64 or 128
   static const int pipe_env = getenv("B200_ATTN_PIPE") ? atoi(getenv("B200_ATTN_PIPE")) : -1;
   const int kv1 = (head_dim <= 48 && kv_env != 128) ? 64 : 128;
-  const int pipe = (variant & 8) ? 0 : (variant & 16) ? 1 : pipe_env >= 0 ? pipe_env : (head_dim >= 64 && seq > kv1) ? 1 : 0;
+  const int pipe = (variant & 8) ? 0 : (variant & 16) ? 1 : pipe_env >= 0 ? pipe_env : ((head_dim >= 64 || head_dim == 32) && seq > kv1) ? 1 : 0;
   const int kv = pipe == 1 ? kv1 / 2 : kv1;
+  // TS form (head_dim 32 / 64): P through TMEM instead of shared memory (B200_ATTN_TS=0 / variant bit 5 turn it off)
+  static const int ts_env = getenv("B200_ATTN_TS") ? atoi(getenv("B200_ATTN_TS")) : 1;
+  const bool ts = (head_dim == 32 || head_dim == 64) && pipe != 2 && ((variant & 64) || (ts_env && !(variant & 32)));
   p.nblk = (seq + kv - 1) / kv;
   int cols = 32;
-  while (cols < (pipe ? 2 : 1) * kv + head_dim + 16) cols *= 2;
+  while (cols < (ts ? (pipe ? 2 : 1) * (kv + kv / 2) + head_dim : (pipe ? 2 : 1) * kv + head_dim + 16)) cols *= 2;
   p.tmem_cols = cols;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
@@ -597,6 +707,13 @@ static int attention_impl(const void* qkv, void* out, float* lse, int batch, int
     if (kv == KVP_) return launch_attention<D_, KVP_, true>(tm, tmkv, qkv, p, stream);                               \
     if (kv == KVP2_) return launch_attention<D_, KVP2_, true>(tm, tmkv, qkv, p, stream);                             \
     return fail(B200_ERR_UNSUPPORTED, "attention: no pipelined kernel for head_dim %d with %d-key blocks", D_, kv);
+  if (ts) {
+    if (head_dim == 32) return pipe ? launch_attention<32, 32, true, true>(tm, tmkv, qkv, p, stream)
+                                    : kv == 64 ? launch_attention<32, 64, false, true>(tm, tmkv, qkv, p, stream)
+                                               : launch_attention<32, 128, false, true>(tm, tmkv, qkv, p, stream);
+    return pipe ? launch_attention<64, 64, true, true>(tm, tmkv, qkv, p, stream)
+                : launch_attention<64, 128, false, true>(tm, tmkv, qkv, p, stream);
+  }
   switch (head_dim) {
     B200_ATTN_CASE(32, 64, 32, 64)
     B200_ATTN_CASE(48, 64, 32, 64)

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """A/B of the attention kernel's forms on the step's shapes (and config 5's): variant 0 = the default
-choice, 8 = the single-buffered form, 16 = the pipelined form (two S / P buffers), +4 flips the packed / fp32 exp2 choice.  Usage: attn_ab.py [variant ...]"""
+choice, 8 = the single-buffered form, 16 = the pipelined form (two S / P buffers), +4 flips the packed / fp32 exp2 choice,
++32 / +64 = P through shared memory / through TMEM (head_dim 32 / 64).  Usage: attn_ab.py [variant ...]"""
 import sys
 from pathlib import Path
 import torch
@@ -10,7 +11,7 @@ from audioldm_with_lora_b200 import ops  # noqa: E402
 
 SHAPES = [(16, 1000, 8, 32), (16, 252, 8, 48), (16, 64, 8, 80), (32, 3000, 8, 64), (32, 752, 8, 96), (32, 188, 8, 160),
           (2, 1, 8, 32), (3, 129, 8, 48), (2, 333, 8, 64)]
-variants = [int(a) for a in sys.argv[1:]] or [8, 16]
+variants = [int(a) for a in sys.argv[1:]] or [8 + 32, 8 + 64, 16 + 32, 16 + 64]
 for b, s, h, d in SHAPES:
     torch.manual_seed(0)
     qkv = (torch.randn(b, s, 3 * h * d, device="cuda") * 1.5).to(torch.bfloat16)
