@@ -51,7 +51,11 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-template <int D, int BC, bool kModeQ>
+// TS: P^T / dS^T go back to tensor memory (bf16 pairs, BC / 2 columns each, behind T1 / T2) and are the TMEM A operands of
+// the accumulating products, instead of 2 x 16 KB of shared-memory stores and tensor-core reads per block (the forward
+// kernel's TS form, attention.cu).  Needs 3 BC + 2 D <= 512 TMEM columns without giving up a co-resident CTA: head_dim 32
+// (BC 64: 256 columns, two CTAs per SM as before) and 64 (BC 128: 512 columns, one CTA either way).
+template <int D, int BC, bool kModeQ, bool TS = false>
 __global__ void __launch_bounds__(kBwdThreads)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                      const __grid_constant__ CUtensorMap tmQKVc, const __grid_constant__ CUtensorMap tmDOc,
@@ -66,7 +70,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint8_t* sX2 = sX1 + kTileBytes;
   uint8_t* sP = sX2 + kTileBytes;               // P^T (mode KV only)
   uint8_t* sDS = sP + kPBytes;                  // dS^T / dS
-  uint8_t* sY = sDS + kPBytes;                  // stages x {Y1, Y2}
+  uint8_t* sY = TS ? sP : sDS + kPBytes;        // stages x {Y1, Y2} (TS: no P^T / dS^T tiles in shared memory)
   float* s_stat = reinterpret_cast<float*>(sY + p.stages * 2 * kYTile);         // [2][128]: lse, delta of the column block
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 256);
   uint64_t* x_full = bars;
@@ -115,8 +119,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   pdl_wait();
   const uint32_t t_1 = tmem_base;                   // T1: columns [0, BC)
   const uint32_t t_2 = tmem_base + BC;              // T2: columns [BC, 2 BC)
-  const uint32_t t_a1 = tmem_base + 2 * BC;         // Acc1 (dV): [2 BC, 2 BC + D)
-  const uint32_t t_a2 = tmem_base + 2 * BC + D;     // Acc2 (dK or dQ): [2 BC + D, 2 BC + 2 D)
+  const uint32_t t_p = tmem_base + 2 * BC;          // TS: P^T as bf16 pairs, BC / 2 columns
+  const uint32_t t_ds = t_p + BC / 2;               // TS: dS^T / dS
+  const uint32_t t_a1 = tmem_base + (TS ? 3 : 2) * BC;      // Acc1 (dV): D columns behind the score (and P / dS) columns
+  const uint32_t t_a2 = t_a1 + D;                   // Acc2 (dK or dQ): the next D columns
 
   if (warp == 4) {
     // ============================================================ TMA producer
@@ -192,14 +198,16 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             for (int k = 0; k < BC / 16; ++k) {
               const uint64_t a_desc = make_smem_desc(p_addr + k * 4096, 2048, 128, SWZ_NONE);
               const uint64_t b_desc = make_smem_desc(y2_addr + k * 256, 128, kChunkY, SWZ_NONE);
-              umma_bf16_ss(t_a1, a_desc, b_desc, idesc_a, (j | k) != 0);
+              if (TS) umma_bf16_ts(t_a1, t_p + k * 8, b_desc, idesc_a, (j | k) != 0);
+              else umma_bf16_ss(t_a1, a_desc, b_desc, idesc_a, (j | k) != 0);
             }
           }
 #pragma unroll
           for (int k = 0; k < BC / 16; ++k) {
             const uint64_t a_desc = make_smem_desc(ds_addr + k * 4096, 2048, 128, SWZ_NONE);
             const uint64_t b_desc = make_smem_desc(y1_addr + k * 256, 128, kChunkY, SWZ_NONE);
-            umma_bf16_ss(t_a2, a_desc, b_desc, idesc_a, (j | k) != 0);
+            if (TS) umma_bf16_ts(t_a2, t_ds + k * 8, b_desc, idesc_a, (j | k) != 0);
+            else umma_bf16_ss(t_a2, a_desc, b_desc, idesc_a, (j | k) != 0);
           }
           umma_commit(&y_empty[s]);
           if (j == p.nblk - 1) umma_commit(acc_full);
@@ -243,6 +251,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         tmem_ld_x32(t_1 + lane_off + c * 32, r1);
         tmem_ld_x32(t_2 + lane_off + c * 32, r2);
         tmem_wait_ld();
+        uint32_t pt[16], dt[16];                  // TS: the chunk's 32 P^T / dS^T values as bf16 pairs
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint32_t pk[4], dk[4];
@@ -262,11 +271,24 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             pk[i] = pack_bf16x2(pv[0], pv[1]);
             dk[i] = pack_bf16x2(dv[0], dv[1]);
           }
-          if (!kModeQ) *reinterpret_cast<uint4*>(sp_row + (c * 4 + g) * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(sds_row + (c * 4 + g) * 2048) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+          if (TS) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              pt[g * 4 + i] = pk[i];
+              dt[g * 4 + i] = dk[i];
+            }
+          } else {
+            if (!kModeQ) *reinterpret_cast<uint4*>(sp_row + (c * 4 + g) * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(sds_row + (c * 4 + g) * 2048) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+          }
+        }
+        if (TS) {
+          if (!kModeQ) tmem_st_x16(t_p + lane_off + c * 16, pt);
+          tmem_st_x16(t_ds + lane_off + c * 16, dt);
         }
       }
-      fence_proxy_async_smem();
+      if (TS) tmem_wait_st();
+      else fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(ps_full);
     }
@@ -334,14 +356,14 @@ attention_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16*
   }
 }
 
-template <int D, int BC>
+template <int D, int BC, bool TS = false>
 static int launch_attention_bwd(const CUtensorMap& tq, const CUtensorMap& td, const CUtensorMap& tqc, const CUtensorMap& tdc,
                                 AttnBwdParams& p, cudaStream_t stream) {
   constexpr int kTileBytes = 128 * D * 2;
   constexpr int kYTile = BC * D * 2;
-  const int fixed = 2 * kTileBytes + 2 * kBT * BC * 2 + 1024 /*stats*/ + 128 /*barriers*/ + 128 /*align*/;
+  const int fixed = 2 * kTileBytes + (TS ? 0 : 2 * kBT * BC * 2) + 1024 /*stats*/ + 128 /*barriers*/ + 128 /*align*/;
   int cols = 32;
-  while (cols < 2 * BC + 2 * D) cols *= 2;
+  while (cols < (TS ? 3 : 2) * BC + 2 * D) cols *= 2;
   p.tmem_cols = cols;
   p.nblk = (p.seq + BC - 1) / BC;
   const int budget = (220 * 1024) / (512 / cols);
@@ -349,16 +371,16 @@ static int launch_attention_bwd(const CUtensorMap& tq, const CUtensorMap& td, co
   const int smem_bytes = fixed + p.stages * 2 * kYTile;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<D, BC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<D, BC, false, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_bwd_kernel<D, BC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(attention_bwd_kernel<D, BC, true, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(B200_ERR_CUDA, "attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
   dim3 grid((p.seq + kBT - 1) / kBT, p.batch * p.heads);
-  B200_CHECK_PDL("attention_bwd(kv)", launch_pdl(attention_bwd_kernel<D, BC, false>, grid, dim3(kBwdThreads), (size_t)smem_bytes,
+  B200_CHECK_PDL("attention_bwd(kv)", launch_pdl(attention_bwd_kernel<D, BC, false, TS>, grid, dim3(kBwdThreads), (size_t)smem_bytes,
                                                  stream, 0, tq, td, tqc, tdc, p));
-  B200_CHECK_PDL("attention_bwd(q)", launch_pdl(attention_bwd_kernel<D, BC, true>, grid, dim3(kBwdThreads), (size_t)smem_bytes,
+  B200_CHECK_PDL("attention_bwd(q)", launch_pdl(attention_bwd_kernel<D, BC, true, TS>, grid, dim3(kBwdThreads), (size_t)smem_bytes,
                                                 stream, 0, tq, td, tqc, tdc, p));
   return B200_OK;
 }
@@ -411,6 +433,9 @@ extern "C" int b200_attention_bwd(const void* qkv, const void* o, const void* do
       if (rc) return rc;
     }
   }
+  static const int ts_env = getenv("B200_ATTN_BWD_TS") ? atoi(getenv("B200_ATTN_BWD_TS")) : 1;     // A/B knob: 0 = P^T / dS^T in smem
+  if (ts_env && head_dim == 32 && bc == 64) return launch_attention_bwd<32, 64, true>(tq, td, tqc, tdc, p, stream);
+  if (ts_env && head_dim == 64) return launch_attention_bwd<64, 128, true>(tq, td, tqc, tdc, p, stream);
   switch (head_dim) {
     case 32: return bc == 64 ? launch_attention_bwd<32, 64>(tq, td, tqc, tdc, p, stream) : launch_attention_bwd<32, 128>(tq, td, tqc, tdc, p, stream);
     case 48: return bc == 64 ? launch_attention_bwd<48, 64>(tq, td, tqc, tdc, p, stream) : launch_attention_bwd<48, 128>(tq, td, tqc, tdc, p, stream);

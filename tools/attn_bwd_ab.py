@@ -11,7 +11,7 @@ import torch.nn.functional as F
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from audioldm_with_lora_b200 import ops  # noqa: E402
 
-for b, s, h, d in [(32, 1024, 8, 32), (32, 256, 8, 48), (32, 64, 8, 80), (8, 3000, 8, 64), (2, 333, 8, 96)]:
+for b, s, h, d in [(32, 1024, 8, 32), (32, 256, 8, 48), (32, 64, 8, 80), (8, 3000, 8, 64), (2, 333, 8, 64), (2, 333, 8, 96)]:
     torch.manual_seed(0)
     C = h * d
     qkv = torch.randn(b, s, 3 * C, device="cuda").to(torch.bfloat16)
