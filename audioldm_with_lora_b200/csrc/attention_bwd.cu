@@ -27,7 +27,11 @@
 namespace b200 {
 
 static constexpr int kBT = 128;                // rows per CTA
-static constexpr int kBwdThreads = 192;        // warps 0-3 elementwise, warp 4 TMA, warp 5 MMA
+// Two elementwise warps per TMEM lane quarter, each taking half of the block's columns (a warp reaches the 32 TMEM lanes
+// warp % 4 owns): 8 instead of 4 elementwise warps per CTA.  With two (or one) CTAs per SM the elementwise pass was bound by
+// the latency of each thread's tcgen05.ld -> exp -> pack -> store chain, not by a pipe.
+static constexpr int kBwdEw = 8;               // elementwise warps
+static constexpr int kBwdThreads = (kBwdEw + 2) * 32;   // warps 0-7 elementwise, warp 8 TMA, warp 9 MMA
 // Columns per streamed block: template parameter BC (128, or 64 for head_dim <= 48: two 64-column score tiles + two
 // accumulators then fit 256 TMEM columns and ~64 KB of shared memory, so two CTAs share an SM and overlap each other's
 // MMA -> elementwise -> MMA hand-offs).
@@ -56,7 +60,7 @@ __device__ __forceinline__ float ex2f(float x) {
 // kernel's TS form, attention.cu).  Needs 3 BC + 2 D <= 512 TMEM columns without giving up a co-resident CTA: head_dim 32
 // (BC 64: 256 columns, two CTAs per SM as before) and 64 (BC 128: 512 columns, one CTA either way).
 template <int D, int BC, bool kModeQ, bool TS = false>
-__global__ void __launch_bounds__(kBwdThreads)
+__global__ void __launch_bounds__(kBwdThreads, ((TS ? 3 : 2) * BC + 2 * D <= 256) ? 2 : 1)      // two CTAs per SM where TMEM allows it
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                      const __grid_constant__ CUtensorMap tmQKVc, const __grid_constant__ CUtensorMap tmDOc,
                      const AttnBwdParams p) {
@@ -103,11 +107,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       mbar_init(&y_empty[i], 1);
     }
     mbar_init(t_full, 1);
-    mbar_init(ps_full, 128);
+    mbar_init(ps_full, kBwdEw * 32);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == kBwdEw) {
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
@@ -124,7 +128,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   const uint32_t t_a1 = tmem_base + (TS ? 3 : 2) * BC;      // Acc1 (dV): D columns behind the score (and P / dS) columns
   const uint32_t t_a2 = t_a1 + D;                   // Acc2 (dK or dQ): the next D columns
 
-  if (warp == 4) {
+  if (warp == kBwdEw) {
     // ============================================================ TMA producer
     // (whole warp, uniform control flow, one lane elected at each use issues -- see conv_gemm.cu)
     {
@@ -159,7 +163,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kBwdEw + 1) {
     // ============================================================ MMA issuer (whole warp, elected lane issues)
     {
       const uint32_t idesc_t = make_idesc_bf16(128, BC, 0, 0);        // T = X Y^T, both K-major
@@ -220,8 +224,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     }
   } else {
     // ============================================================ elementwise warps (row = thread)
-    const int row = warp * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const int quarter = warp & 3, half = warp >> 2;      // TMEM lane quarter; which half of the block's columns
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     uint8_t* sp_row = sP + row * 16;
     uint8_t* sds_row = sDS + row * 16;
     const size_t stat_base = (static_cast<size_t>(b) * p.heads + h) * p.seq;
@@ -234,19 +239,19 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       const int cvalid = min(BC, p.seq - j * BC);
       if (!kModeQ) {
         // statistics of this block's BC columns (= queries); the previous block's readers are past ps_full
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kBwdEw * 32);
         const int col = j * BC + row;
-        if (row < BC) {
+        if (half == 0 && row < BC) {
           s_stat[row] = col < p.seq ? p.lse[stat_base + col] : 0.f;
           s_stat[128 + row] = col < p.seq ? p.delta[stat_base + col] : 0.f;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kBwdEw * 32);
       }
       // T1 / T2 of this block are complete; every earlier MMA (incl. the previous block's reads of sP / sDS) too
       mbar_wait(t_full, j & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BC / 32; ++c) {
+      for (int c = half * (BC / 64); c < (half + 1) * (BC / 64); ++c) {
         uint32_t r1[32], r2[32];
         tmem_ld_x32(t_1 + lane_off + c * 32, r1);
         tmem_ld_x32(t_2 + lane_off + c * 32, r2);
@@ -306,6 +311,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       __nv_bfloat16* o = orow + (kModeQ ? 0 : (which == 0 ? 2 * C : C));
 #pragma unroll
       for (int c = 0; c < D / 16; ++c) {
+        if ((c & 1) != half) continue;              // the two warps of a lane quarter split the accumulator's column chunks
         uint32_t r[16];
         tmem_ld_x16(t_acc + c * 16, r);
         tmem_wait_ld();
@@ -326,7 +332,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   }
 
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kBwdEw) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
