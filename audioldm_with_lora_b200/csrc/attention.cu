@@ -15,6 +15,13 @@
 //                 from exactly the bf16 probabilities the numerator uses.
 // With d = 32 the kernel is bound by the softmax instruction stream (exp throughput), not by the tensor pipe:
 // the structure above removes the second pass over S, the per-block O fold and the row-sum adds.
+//
+// Forms (template parameters; the host picks per head_dim / sequence, profiles/r02_attn_pipe.md):
+//   PIPE  software-pipelined: two S buffers in TMEM (and two P buffers), QK^T issued two key blocks ahead of P V, half as
+//         many keys per block (same TMEM columns, same CTAs per SM).  Default for head_dim 32 and >= 64.
+//   TS    head_dim 32 / 64: Q, K AND V arrive as whole swizzled rows (V = the canonical MN-major swizzled operand), the
+//         bf16 probabilities go back to TMEM (tcgen05.st) and P V takes its A operand from there, the denominator is an
+//         fp32 register sum: no P tile and no ones columns in shared memory.
 // Q/K/V tiles are fetched by TMA directly from the fused-QKV activation [B, S, 3C] with a 4-D tensor
 // map (8 elems, rows, 16-byte channel chunks, batch): the box lands as 8x16B core matrices, i.e. the
 // no-swizzle UMMA canonical layout, for any head_dim that is a multiple of 16 (32/48/80 for
